@@ -1,0 +1,179 @@
+"""Circuit builders shared by the golden generator, the oracle tests and the GPU parity tests.
+
+Each builder takes any object with the reference's ``Netlist.add_*`` API (the reference's
+``yalrf.Netlist``, the oracle's ``FlatNetlist`` or the product's ``yalrf_b200.Netlist``) and
+returns a dict of the device handles a sweep mutates.  Netlists follow the reference scripts
+cited in each docstring (paths relative to the reference checkout).
+"""
+import numpy as np
+
+
+def hb_diode(y, ac=5.0):
+    """tests/HB_Diode.py:10-21 -- BASELINE config 1."""
+    i1 = y.add_iac('I1', 'nx', 'gnd', ac=ac, freq=1e6)
+    y.add_gyrator('G1', 'nx', 'n1', 'gnd', 'gnd', 1)
+    y.add_resistor('R1', 'n1', 'n2', 100)
+    d1 = y.add_diode('D1', 'gnd', 'n2')
+    d1.options['Is'] = 1e-15
+    d1.options['N'] = 1
+    d1.options['Area'] = 1
+    return dict(i1=i1, d1=d1, freq=1e6, K=10)
+
+
+def hb_diode_two_tones(y, ac=1.0):
+    """tests/HB_DiodeTwoTones.py:11-22 -- BASELINE config 3 (run with [3,3] or [8,8])."""
+    i1 = y.add_iac('I1', 'nx', 'gnd', ac=ac, freq=1.1e6)
+    y.add_gyrator('G1', 'nx', 'nz', 'gnd', 'gnd', 1)
+    i2 = y.add_iac('I2', 'ny', 'gnd', ac=ac, freq=0.9e6)
+    y.add_gyrator('G2', 'ny', 'n1', 'nz', 'gnd', 1)
+    y.add_resistor('R1', 'n1', 'n2', 100)
+    d1 = y.add_diode('D1', 'n2', 'gnd')
+    d1.options['Is'] = 1e-15
+    d1.options['N'] = 1
+    d1.options['Area'] = 1
+    return dict(i1=i1, i2=i2, d1=d1, freq=[1.1e6, 0.9e6])
+
+
+def peltz(y, c=10e-9):
+    """tests/HBOsc_Peltz.py:13-45 / README example -- BASELINE config 2."""
+    vcc, r, l, re = 10, 200e3, 0.5e-3, 50e3
+    y.add_idc('I1', 'nx', 'gnd', dc=vcc)
+    y.add_gyrator('G1', 'nx', 'nvcc', 'gnd', 'gnd', 1)
+    y.add_resistor('R1', 'nvcc', 'nb', r)
+    y.add_inductor('L1', 'nvcc', 'nb', l)
+    c1 = y.add_capacitor('C1', 'nvcc', 'nb', c)
+    y.add_resistor('RE', 'ne', 'gnd', re)
+    q1 = y.add_bjt('Q1', 'nb', 'nvcc', 'ne')
+    q2 = y.add_bjt('Q2', 'nvcc', 'nb', 'ne')
+    q1.options['Is'] = 1e-16
+    q1.options['Bf'] = 200
+    q1.options['Br'] = 1
+    q2.options = q1.options.copy()
+    return dict(c1=c1, q1=q1, q2=q2, f0=80e3, V0=0.1, K=10, node='nb')
+
+
+def diffamp(y, vin=60e-3, vbias=1.2):
+    """tests/HB_DiffAmp.py:13-69 -- BASELINE config 4, reference-pinned (resistor loads).
+
+    The sweep of tests/HB_DiffAmp.py:113-117 sets I2.ac = I4.ac = vin / 2.
+    """
+    ibias, vcc, rload = 50e-3, 5, 50
+    y.add_idc('I1', 'nx', 'gnd', dc=vcc)
+    y.add_gyrator('G1', 'nx', 'nvcc', 'gnd', 'gnd', 1)
+    i2 = y.add_iac('I2', 'ny', 'gnd', ac=vin, phase=0, freq=10e6)
+    i3 = y.add_idc('I3', 'ny', 'gnd', dc=vbias)
+    y.add_gyrator('G2', 'ny', 'nb1', 'gnd', 'gnd', 1)
+    i4 = y.add_iac('I4', 'nz', 'gnd', ac=vin, phase=+180, freq=10e6)
+    i5 = y.add_idc('I5', 'nz', 'gnd', dc=vbias)
+    y.add_gyrator('G3', 'nz', 'nb2', 'gnd', 'gnd', 1)
+    y.add_resistor('R1', 'nvcc', 'nc1', rload)
+    y.add_resistor('R2', 'nvcc', 'nc2', rload)
+    q1 = y.add_bjt('Q1', 'nb1', 'nc1', 'ne')
+    q2 = y.add_bjt('Q2', 'nb2', 'nc2', 'ne')
+    q3 = y.add_bjt('Q3', 'nbx', 'ne', 'gnd')
+    q4 = y.add_bjt('Q4', 'nbx', 'nbx', 'gnd')
+    y.add_idc('I6', 'nbx', 'gnd', dc=ibias)
+    o = q1.options
+    o['Is'] = 8.11e-14
+    o['Nf'] = 1
+    o['Nr'] = 1
+    o['Ikf'] = 0.5
+    o['Ikr'] = 0.226
+    o['Vaf'] = 113
+    o['Var'] = 24
+    o['Ise'] = 1.06e-11
+    o['Ne'] = 2
+    o['Isc'] = 0
+    o['Nc'] = 2
+    o['Bf'] = 205
+    o['Br'] = 4
+    o['Cje'] = 2.95e-11
+    o['Cjc'] = 1.52e-11
+    o['Cjs'] = 0.
+    q2.options = q1.options
+    q3.options = q1.options
+    q4.options = q1.options
+    return dict(i2=i2, i3=i3, i4=i4, i5=i5, q=[q1, q2, q3, q4], freq=10e6, K=10)
+
+
+def diffamp_activeload(y, vin=60e-3, vbias=1.5):
+    """tests/HB_DiffAmp_ActiveLoad.py:17-54 -- BASELINE config 4 netlist (PNP active loads).
+
+    The reference runs only DC on it; its HB treats PNP as NPN and diverges.
+    Usable for HB only with the PNP polarity extension.
+    """
+    ibias, vcc = 10e-3, 5
+    y.add_idc('I1', 'nx', 'gnd', dc=vcc)
+    y.add_gyrator('G1', 'nx', 'nvcc', 'gnd', 'gnd', 1)
+    i2 = y.add_iac('I2', 'ny', 'gnd', ac=vin, phase=0, freq=10e6)
+    i3 = y.add_idc('I3', 'ny', 'gnd', dc=vbias)
+    y.add_gyrator('G2', 'ny', 'nb1', 'gnd', 'gnd', 1)
+    i4 = y.add_iac('I4', 'nz', 'gnd', ac=vin, phase=+180, freq=10e6)
+    i5 = y.add_idc('I5', 'nz', 'gnd', dc=vbias)
+    y.add_gyrator('G3', 'nz', 'nb2', 'gnd', 'gnd', 1)
+    q1 = y.add_bjt('Q1', 'nb1', 'nc1', 'ne')
+    q2 = y.add_bjt('Q2', 'nb2', 'nc2', 'ne')
+    q5 = y.add_bjt('Q5', 'nc1', 'nc1', 'nvcc', ispnp=True)
+    q6 = y.add_bjt('Q6', 'nc1', 'nc2', 'nvcc', ispnp=True)
+    q3 = y.add_bjt('Q3', 'nbx', 'ne', 'gnd')
+    q4 = y.add_bjt('Q4', 'nbx', 'nbx', 'gnd')
+    y.add_idc('I6', 'nbx', 'gnd', dc=ibias)
+    q1.options['Is'] = 1e-15
+    q1.options['Bf'] = 100
+    q1.options['Vaf'] = 60
+    for q in (q2, q3, q4, q5, q6):
+        q.options = q1.options
+    return dict(i2=i2, i3=i3, i4=i4, i5=i5, q=[q1, q2, q3, q4, q5, q6], freq=10e6, K=10)
+
+
+def hb_bjt(y):
+    """tests/HB_BJT.py:10-30 -- single common-emitter stage (junction capacitances off)."""
+    f = 10e6
+    y.add_iac('I1', 'n1', 'gnd', ac=10e-3, freq=f)
+    y.add_idc('I2', 'n1', 'gnd', dc=10e-3)
+    y.add_idc('I3', 'n2', 'gnd', dc=20e-3)
+    y.add_resistor('R1', 'n1', 'gnd', 1e3)
+    y.add_resistor('R2', 'n1', 'nb', 1e3)
+    y.add_resistor('R3', 'n2', 'gnd', 100)
+    y.add_resistor('R4', 'n2', 'nc', 1e3)
+    y.add_resistor('R5', 'ne', 'gnd', 1e3)
+    q1 = y.add_bjt('Q1', 'nb', 'nc', 'ne')
+    q1.options['Is'] = 1e-15
+    q1.options['Bf'] = 100
+    q1.options['Br'] = 1
+    return dict(q1=q1, freq=f, K=10)
+
+
+def vanderpol(y, alpha=1):
+    """tests/HBOsc_VanDerPol.py:10-21 -- cubic nonlinearity oscillator."""
+    y.add_inductor('L', 'np', 'gnd', 1)
+    y.add_capacitor('C', 'np', 'gnd', 1)
+    r = y.add_resistor('R', 'np', 'gnd', -1 / alpha)
+    x = y.add_cubicnl('X1', 'np', 'gnd', alpha)
+    return dict(r=r, x=x, f0=0.13, V0=1.2, K=20, node='np')
+
+
+def ladder(y, stages=8, cje=0.0, seed=0, ac=1.0):
+    """BASELINE config 5: two-tone source stack into a diode / diode-connected-BJT ladder."""
+    rng = np.random.default_rng(seed)
+    y.add_iac('I1', 'nx', 'gnd', ac=ac, freq=1.1e6)
+    y.add_gyrator('G1', 'nx', 'nz', 'gnd', 'gnd', 1)
+    y.add_iac('I2', 'ny', 'gnd', ac=ac, freq=0.9e6)
+    y.add_gyrator('G2', 'ny', 'n0', 'nz', 'gnd', 1)
+    devs = []
+    for i in range(1, stages + 1):
+        y.add_resistor('R%d' % i, 'n%d' % (i - 1), 'n%d' % i, 100)
+        jitter = float(10.0 ** rng.uniform(np.log10(0.9), np.log10(1.1)))
+        if i % 2 == 1:
+            d = y.add_diode('D%d' % i, 'n%d' % i, 'gnd')
+            d.options['Is'] = 1e-15 * jitter
+        else:
+            d = y.add_bjt('Q%d' % i, 'n%d' % i, 'n%d' % i, 'gnd')
+            d.options['Is'] = 1e-15 * jitter
+            d.options['Bf'] = 100
+            d.options['Cje'] = cje
+            # Itf = 0 (default) makes If / (If + Itf) = 0/0 = NaN at the zero-bias start (BJT.py:556): the
+            # reference itself cannot start this ladder without it.  Tf = 0, so Itf changes nothing else.
+            d.options['Itf'] = 1e-3
+        devs.append(d)
+    return dict(devs=devs, freq=[1.1e6, 0.9e6])
