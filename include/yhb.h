@@ -1,0 +1,187 @@
+/*
+ * yhb.h -- C ABI of the B200-native harmonic-balance engine (libyhb.so).
+ *
+ * The reference (victorpreuss/YalRF) is pure Python and has no FFI: its boundary for this path is
+ * the object surface MultiToneHarmonicBalance.run / hb_loop / run_oscillator
+ * (yalrf/Analyses/MultiToneHarmonicBalance.py:137-631) fed by Netlist.add_* (yalrf/Netlist.py:31-694).
+ * The entry points below are what a ctypes binding inside that class would call instead of its own
+ * numpy loop; each one cites the reference code it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - All arrays are fp64 / int32, circuit-major ("[B][...]" = B circuits of one batch, contiguous).
+ *   - Node indices follow the reference: 0 = 'gnd', 1..N = Netlist.add_node order (Netlist.py:703-725).
+ *   - The unknown vector V is the reference's layout (MultiToneHarmonicBalance.py:351-352, 398-400):
+ *     W = N*S reals, node-major, row n*S = DC, n*S+2k-1 = Re, n*S+2k = Im of harmonic k, S = 2K+1.
+ *   - Device entry points take DEVICE pointers and a cudaStream_t (passed as void*); they never
+ *     synchronise the device unless stated.  *_host entry points take HOST pointers and do their own
+ *     copies.  Return value: 0 = ok, negative = error (text via yhb_last_error()).  Non-convergence of
+ *     a circuit is data (converged[b] = 0), not an error -- as in the reference (:386-387).
+ *   - There is no CPU fallback: every entry point that computes needs a CUDA device.
+ */
+#ifndef YHB_H
+#define YHB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YHB_VERSION 100
+
+/* linear element kinds: the classes that implement add_mthb_stamps (MultiToneHarmonicBalance.py:686-695) */
+enum {
+    YHB_LIN_RESISTOR = 0,  /* Resistor.py:43-65;   val[0] = R                                  */
+    YHB_LIN_CAPACITOR = 1, /* Capacitor.py:62-85;  val[0] = C   (1e-12 S at DC)                */
+    YHB_LIN_INDUCTOR = 2,  /* Inductor.py:64-87;   val[0] = L   (1e6 S at DC, no branch row)   */
+    YHB_LIN_GYRATOR = 3,   /* Gyrator.py:38-73;    val[0] = G   (HB stamps hard-code 1; DC uses G) */
+    YHB_LIN_IHF = 4        /* IdealHarmonicFilter.py:33-57; val[0] = freq, val[1] = g          */
+};
+
+/* independent current sources, consumed by calc_Is (MultiToneHarmonicBalance.py:647-684) */
+enum {
+    YHB_SRC_DC = 0,  /* itype == 'dc': val = (dc, -, -)                                             */
+    YHB_SRC_AC1 = 1, /* itype == 'ac', freq == f1: val = (-, ac*cos(phase), ac*sin(phase))          */
+    YHB_SRC_AC2 = 2, /* itype == 'ac', freq == f2 (two-tone only)                                   */
+    YHB_SRC_DC_ONLY = 3 /* itype == 'both' (Netlist.add_isource): stamped by the DC analysis
+                           (CurrentSource.py:23-26), ignored by calc_Is (:652, :675)                  */
+};
+
+/* raw diode model parameters, Diode.options (Diode.py:6-36); get_mthb_params uses the raw values */
+enum {
+    YHB_DIODE_TEMP = 0, YHB_DIODE_IS, YHB_DIODE_N, YHB_DIODE_ISR, YHB_DIODE_NR, YHB_DIODE_IKF,
+    YHB_DIODE_BV, YHB_DIODE_IBV, YHB_DIODE_RS, YHB_DIODE_AREA, YHB_DIODE_NPAR
+};
+
+/* raw BJT model parameters, BJT.options (BJT.py:5-52) + polarity (BJT.py:71) */
+enum {
+    YHB_BJT_TEMP = 0, YHB_BJT_IS, YHB_BJT_NF, YHB_BJT_NR, YHB_BJT_IKF, YHB_BJT_IKR, YHB_BJT_VAF,
+    YHB_BJT_VAR, YHB_BJT_ISE, YHB_BJT_NE, YHB_BJT_ISC, YHB_BJT_NC, YHB_BJT_BF, YHB_BJT_BR,
+    YHB_BJT_CJE, YHB_BJT_VJE, YHB_BJT_MJE, YHB_BJT_CJC, YHB_BJT_VJC, YHB_BJT_MJC, YHB_BJT_XCJC,
+    YHB_BJT_CJS, YHB_BJT_VJS, YHB_BJT_MJS, YHB_BJT_FC, YHB_BJT_TF, YHB_BJT_XTF, YHB_BJT_VTF,
+    YHB_BJT_ITF, YHB_BJT_TR, YHB_BJT_AREA, YHB_BJT_TYPE /* +1 npn, -1 pnp */, YHB_BJT_NPAR
+};
+
+#define YHB_FLAG_PNP_EXTENSION 1  /* honour BJT polarity in HB (the reference ignores it, BJT.py:495-503) */
+#define YHB_FLAG_EXACT_JACOBIAN 2 /* re-zero dQdV every iteration (the reference accumulates it, :413/:438) */
+
+#define YHB_MAX_LEVELS 64 /* hb_loop calls recorded per solve: 1 direct attempt + <=50 continuation levels */
+
+typedef struct yhb_plan yhb_plan; /* opaque: topology + tables, immutable, shareable across streams */
+
+/* Topology of one netlist shape (what Netlist + run()'s setup :234-302 determine).  Host pointers. */
+typedef struct {
+    int32_t num_nodes; /* N: non-ground nodes */
+    int32_t num_tones; /* 1: K = K1 (:247-251); 2: box truncation K = (2 K2 + 1) K1 + K2 (:252-273) */
+    int32_t K1, K2;
+    int32_t num_lin;
+    const int32_t *lin_kind;  /* [num_lin]    */
+    const int32_t *lin_nodes; /* [num_lin][4] */
+    int32_t num_src;
+    const int32_t *src_kind;  /* [num_src]    */
+    const int32_t *src_nodes; /* [num_src][2] */
+    int32_t num_diode;
+    const int32_t *diode_nodes; /* [num_diode][2]  anode, cathode */
+    int32_t num_bjt;
+    const int32_t *bjt_nodes; /* [num_bjt][3]  B, C, E (substrate is forced to 0 V, :504) */
+    int32_t num_cubic;
+    const int32_t *cubic_nodes; /* [num_cubic][2] */
+    /* optional netlist order of the nonlinear devices (get_nonlinear_devices, Netlist.py:791-797), which fixes
+     * the floating-point summation order of shared stamps: kind 0 = diode, 1 = bjt, 2 = cubic, index into the
+     * tables above; [num_diode + num_bjt + num_cubic] each.  NULL = diodes, cubics, bjts. */
+    const int32_t *nl_kind;
+    const int32_t *nl_index;
+    const double *idft; /* optional [S][S] row-major table as built at :294-300; NULL = analytic */
+    const double *dft;  /* optional [S][S] = inv(idft) as at :302; NULL = analytic inverse       */
+    int32_t flags;
+} yhb_plan_desc;
+
+/* Per-circuit parameters, re-read at every run (users mutate device objects between runs). */
+typedef struct {
+    int32_t batch;
+    const double *tones;     /* [B][2]  f1, f2 (f2 ignored for one tone) */
+    const double *lin_val;   /* [B][num_lin][2]   */
+    const double *src_val;   /* [B][num_src][3]   dc, ac_re, ac_im */
+    const double *diode_par; /* [B][num_diode][YHB_DIODE_NPAR] */
+    const double *bjt_par;   /* [B][num_bjt][YHB_BJT_NPAR]     */
+    const double *cubic_par; /* [B][num_cubic]   alpha */
+} yhb_params;
+
+/* MultiToneHarmonicBalance.options (:18-21) */
+typedef struct {
+    double reltol;
+    double abstol;
+    int32_t maxiter;
+    int32_t reserved;
+} yhb_options;
+
+/* Results of a solve.  Any pointer may be NULL to skip that output. */
+typedef struct {
+    double *V;             /* [B][W]  in: start vector when have_v0, out: hb.V (:393)                  */
+    double *Vf;            /* [B][N][K+1][2]  complex phasors hb.Vf (:396-403)                         */
+    int32_t *converged;    /* [B]                                                                     */
+    int32_t *newton_iters; /* [B]  Newton iterations over all hb_loop calls                            */
+    int32_t *lu_count;     /* [B]  LU factorisations                                                   */
+    int32_t *level_iters;  /* [B][YHB_MAX_LEVELS]  'NR number of iterations' of each hb_loop call, 0-terminated */
+    double *level_alpha;   /* [B][YHB_MAX_LEVELS]  'Alpha level' of each call (1.0 for the direct attempt) */
+    double *err;           /* [B]  'HB total error' sum|F| of the last hb_loop call (:597)             */
+} yhb_result;
+
+const char *yhb_last_error(void);
+int yhb_version(void);
+/* CUDA device used by the calling thread for all later calls (cudaSetDevice) */
+int yhb_set_device(int32_t device);
+
+/* plan = the setup part of run() (:234-302): grid sizes, DFT/IDFT tables, stamp tables */
+int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out);
+void yhb_plan_destroy(yhb_plan *plan);
+int yhb_plan_dims(const yhb_plan *plan, int32_t *N, int32_t *K, int32_t *S, int32_t *W);
+/* real frequency of each bin of circuit tones (f1, f2), as self.freqs (:251, :271): host helper */
+int yhb_plan_freqs(const yhb_plan *plan, double f1, double f2, double *freqs /* [K+1] */);
+
+/* bytes of device scratch the solve entry points need for a batch of this size */
+size_t yhb_workspace_bytes(const yhb_plan *plan, int32_t batch);
+
+/* calc_V0 (:697-704) = DC.run (DC.py:54-123): batched DC operating points, Vdc[B][N] node voltages.
+ * dc_info[B][2] = (converged, Newton iterations). */
+int yhb_dc_solve(const yhb_plan *plan, const yhb_params *p, void *ws, size_t ws_bytes, double *Vdc,
+                 int32_t *dc_info, void *stream);
+
+/* run() (:234-405): optional direct attempt from V0, then the source-stepping ladder (:338-384) from
+ * the DC point; every hb_loop (:407-631) runs on the GPU.  have_v0 != 0: res->V holds the start.
+ * Vdc[B][N]: DC node voltages (from yhb_dc_solve), used for cold starts and after a failed direct attempt. */
+int yhb_solve(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt, void *ws,
+              size_t ws_bytes, int32_t have_v0, const double *Vdc, const yhb_result *res, void *stream);
+
+/* one hb_loop (:407-631) at source-stepping factor alpha[B] from res->V */
+int yhb_newton(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt, void *ws,
+               size_t ws_bytes, const double *alpha, const yhb_result *res, void *stream);
+
+/* Whole run() for a batch with HOST buffers: H2D of the parameters, DC points, solve, D2H of the results,
+ * synchronous.  V0 (host, [B][W]) may be NULL for cold starts.  This is the end-to-end entry. */
+int yhb_run_host(const yhb_plan *plan, const yhb_params *host_params, const yhb_options *opt,
+                 const double *V0, const yhb_result *host_res);
+
+/* ---- stage entry points (parity tests / profiling); device pointers -------------------------------- */
+/* ifft (:706-713): vt[B][W] = IDFT applied per node */
+int yhb_stage_ifft(const yhb_plan *plan, int32_t batch, const double *V, double *vt, void *stream);
+/* device sweep (:441-570) on time samples: per-sample model outputs.
+ * diode_out[B][num_diode][2][S] = (gd, Id); cubic_out[B][num_cubic][2][S] = (g, I);
+ * bjt_out[B][num_bjt][14][S] in get_hb_params order (BJT.py:582). vtprev = previous iterate's samples. */
+int yhb_stage_device_eval(const yhb_plan *plan, const yhb_params *p, const double *vt,
+                          const double *vtprev, double *diode_out, double *bjt_out, double *cubic_out,
+                          void *stream);
+/* residual + Jacobian (:572-588) for iterate V with limiter reference vtprev and source factor alpha:
+ * J[B][W][W] row-major, F[B][W].  cacc (may be NULL) = accumulated capacitance waveforms
+ * [B][num_bjt][4][S] in/out (the reference's never-reset dQdV, :413). */
+int yhb_stage_assemble(const yhb_plan *plan, const yhb_params *p, void *ws, size_t ws_bytes,
+                       const double *V, const double *vtprev, const double *alpha, double *cacc,
+                       double *J, double *F, void *stream);
+/* LU with partial pivoting + solve (:620-621): x[B][W] = J^-1 F; J is overwritten by its factors */
+int yhb_stage_lu(int32_t batch, int32_t W, double *J, const double *F, double *x, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YHB_H */

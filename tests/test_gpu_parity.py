@@ -1,0 +1,185 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures written by the unmodified
+reference (tests/golden/) and against the numpy oracle on the same inputs.  Run on the B200 box:
+    python -m pytest tests -m gpu -q
+Tolerances: 1e-9 relative on converged phasors (BASELINE.json north_star); per-level Newton iteration
+counts must be identical."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import circuits
+
+pytestmark = pytest.mark.gpu
+
+
+def relmax(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+@pytest.fixture(scope='module')
+def yb():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    import yalrf_b200
+    return yalrf_b200
+
+
+def mthb(*a, **k):
+    from yalrf_b200.Analyses import MultiToneHarmonicBalance
+    return MultiToneHarmonicBalance(*a, **k)
+
+
+# ----------------------------------------------------------------------------- DC operating point
+@pytest.mark.parametrize('name', ['hb_diode', 'diffamp', 'peltz', 'hb_bjt', 'diffamp_activeload', 'vanderpol'])
+def test_dc_vs_oracle(yb, name):
+    from oracle import hb_oracle as ho
+    from yalrf_b200.Analyses import DC
+    build = getattr(circuits, name)
+    y = yb.Netlist('x')
+    build(y)
+    x = DC('dc').run(y)
+    yo = ho.FlatNetlist()
+    build(yo)
+    xo = ho.DCOracle(yo).run()
+    n = y.get_num_nodes() - 1
+    assert np.max(np.abs(x[:n, 0] - xo[:n, 0])) <= 1e-10 * max(1.0, np.max(np.abs(xo[:n, 0])))
+
+
+# ----------------------------------------------------------------------------- config 1
+@pytest.mark.parametrize('tag,ac,opts', [('hb_diode', 5.0, {}), ('hb_diode_tight', 5.0, {'reltol': 1e-9, 'abstol': 1e-12}),
+                                         ('hb_diode_ac0p5', 0.5, {}), ('hb_diode_ac2', 2.0, {})])
+def test_hb_diode(yb, golden, tag, ac, opts):
+    g = golden(tag)
+    y = yb.YalRF('Diode Testbench')
+    h = circuits.hb_diode(y, ac=ac)
+    hb = mthb('HB1', h['freq'], h['K'])
+    hb.options.update(opts)
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv
+    assert hb.last.levels() == g['iters'].tolist()
+    np.testing.assert_allclose(hb.last.level_alpha[0][:len(g['alphas'])], g['alphas'], rtol=1e-15)
+    assert relmax(hb.V, g['V']) < 1e-9
+    assert relmax(Vf, g['Vf']) < 1e-9
+    np.testing.assert_array_equal(freqs, g['freqs'])
+    assert hb.V.shape == (hb.W, 1) and Vf.shape == (hb.N, hb.K + 1)
+
+
+# ----------------------------------------------------------------------------- config 3
+@pytest.mark.parametrize('tag,nh', [('two_tones_3x3', [3, 3]), ('two_tones_8x8', [8, 8])])
+def test_two_tones(yb, golden, tag, nh):
+    g = golden(tag)
+    y = yb.YalRF('Diode Testbench')
+    h = circuits.hb_diode_two_tones(y)
+    hb = mthb('HB1', h['freq'], nh)
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv
+    assert hb.last.levels() == g['iters'].tolist()
+    np.testing.assert_allclose(freqs, g['freqs'], rtol=1e-15)
+    assert relmax(hb.V, g['V']) < 1e-9
+    assert relmax(Vf, g['Vf']) < 1e-9
+
+
+def test_hb_bjt(yb, golden):
+    g = golden('hb_bjt')
+    y = yb.YalRF('bjt')
+    h = circuits.hb_bjt(y)
+    hb = mthb('HB1', h['freq'], h['K'])
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv
+    assert hb.last.levels() == g['iters'].tolist()
+    assert relmax(hb.V, g['V']) < 1e-9
+
+
+# ----------------------------------------------------------------------------- config 4 (reference-pinned)
+def test_diffamp_cold_grid_batched(yb, golden):
+    """The 12 cold starts of the fixture solved as ONE batch (run_sweep) == 12 reference hb.run(y) calls."""
+    g = golden('diffamp_cold_grid')
+    y = yb.YalRF('Differential Amplifier')
+    h = circuits.diffamp(y)
+    vb, vin = np.meshgrid(g['vbs'], g['vins'], indexing='ij')
+    vb, vin = vb.ravel(), vin.ravel()
+    hb = mthb('HB1', h['freq'], h['K'])
+    res = hb.run_sweep(y, [(h['i2'], 'ac', vin / 2), (h['i4'], 'ac', vin / 2), (h['i3'], 'dc', vb), (h['i5'], 'dc', vb)])
+    for k in range(len(vb)):
+        assert bool(res.converged[k]) == bool(g['converged'][k])
+        its = g['iters'][k]
+        assert res.levels(k) == its[its > 0].tolist(), (k, vb[k], vin[k])
+        assert relmax(res.V[k], g['V'][k][:, 0]) < 1e-9, (k, vb[k], vin[k])
+        for n in range(res.Vf.shape[1]):
+            assert relmax(res.Vf[k, n], g['Vf'][k][n]) < 1e-9
+
+
+def test_diffamp_warm_sweep(yb, golden):
+    """tests/HB_DiffAmp.py:110-121 verbatim: sequential warm-start chain through hb.run(y, V0)."""
+    g = golden('diffamp_warm_sweep')
+    y = yb.YalRF('Differential Amplifier')
+    h = circuits.diffamp(y)
+    hb = mthb('HB1', h['freq'], h['K'])
+    V0 = None
+    for k, vin in enumerate(g['vins']):
+        h['i2'].ac = vin / 2
+        h['i4'].ac = vin / 2
+        conv, freqs, Vf, _, _ = hb.run(y, V0)
+        V0 = hb.V
+        assert conv
+        its = g['iters'][k]
+        assert hb.last.levels() == its[its > 0].tolist()
+        assert relmax(hb.V, g['V'][k]) < 1e-9
+        assert relmax(Vf, g['Vf'][k]) < 1e-9
+
+
+def test_peltz_probe_fixed(yb, golden):
+    g = golden('peltz_probe_fixed')
+    y = yb.Netlist('Oscillator')
+    circuits.peltz(y)
+    y.add_iac('P.I', 'P.n1', 'gnd', ac=0.7, freq=71e3)
+    y.add_gyrator('P.G', 'P.n1', 'P.n2', 'gnd', 'gnd', 1)
+    y.add_idealharmonicfilter('P.IHF', 'P.n2', 'nb', 71e3)
+    hb = mthb('HB1', 71e3, 10)
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv
+    assert hb.last.levels() == g['iters'].tolist()
+    assert relmax(hb.V, g['V']) < 1e-9
+
+
+def test_ladder(yb, golden):
+    g = golden('ladder8_2x2')
+    y = yb.Netlist('ladder')
+    h = circuits.ladder(y, stages=8, cje=0.0)
+    hb = mthb('HB1', h['freq'], [2, 2])
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv == bool(g['converged'])
+    assert hb.last.levels() == g['iters'].tolist()
+    assert relmax(hb.V, g['V']) < 1e-9
+
+
+def test_pnp_extension_vs_oracle(yb):
+    """ActiveLoad netlist with the PNP polarity extension (parity unpinned by reference HB): oracle with the same
+    extension, vin = 100 uV and 1 mV."""
+    from oracle import hb_oracle as ho
+    for vin in (100e-6, 1e-3):
+        y = yb.YalRF('x')
+        h = circuits.diffamp_activeload(y, vin=vin / 2)
+        hb = mthb('HB1', h['freq'], h['K'])
+        hb.pnp_extension = True
+        conv, freqs, Vf, _, _ = hb.run(y)
+        yo = ho.FlatNetlist()
+        ho_h = circuits.diffamp_activeload(yo, vin=vin / 2)
+        o = ho.HBOracle('HB1', ho_h['freq'], ho_h['K'], pnp_extension=True)
+        conv_o, _, Vf_o, _, _ = o.run(yo)
+        assert conv == conv_o
+        assert hb.last.levels() == [l[1] for l in o.level_log]
+        if conv:
+            assert relmax(hb.V, o.V) < 1e-9
+
+
+def test_nonconvergence_is_data(yb):
+    """Unmodified-reference behaviour on the ActiveLoad netlist (PNP treated as NPN): no exception, converged False."""
+    y = yb.YalRF('x')
+    h = circuits.diffamp_activeload(y)
+    hb = mthb('HB1', h['freq'], 2)
+    hb.options['maxiter'] = 20
+    out = hb.run(y)
+    assert out == (False, None, None, None, None)

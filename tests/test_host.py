@@ -1,0 +1,111 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/yhb.h declares, the host mirror of the
+reference interface behaves like the reference's classes, and nothing computes without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import circuits
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    import ctypes
+    from yalrf_b200 import _lib
+    lib = _lib.lib()
+    hdr = open(os.path.join(ROOT, 'include', 'yhb.h')).read()
+    names = set(re.findall(r'\b(yhb_[a-z_0-9]+)\s*\(', hdr))
+    assert names >= set(_lib.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.yhb_version() == 100
+    assert _lib.DIODE_NPAR == 10 and _lib.BJT_NPAR == 32
+
+
+def test_header_enums_match_binding():
+    from yalrf_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'yhb.h')).read()
+    body = re.search(r'YHB_BJT_TEMP = 0,(.*?)YHB_BJT_NPAR', hdr, re.S).group(1)
+    names = ['Temp'] + [x.strip().split('_')[-1].capitalize() for x in re.findall(r'YHB_BJT_[A-Z]+', body)]
+    assert [n.lower() for n in names] == [n.lower() for n in _lib.BJT_PARAMS]
+    body = re.search(r'YHB_DIODE_TEMP = 0,(.*?)YHB_DIODE_NPAR', hdr, re.S).group(1)
+    names = ['Temp'] + [x.strip().split('_')[-1].capitalize() for x in re.findall(r'YHB_DIODE_[A-Z]+', body)]
+    assert [n.lower() for n in names] == [n.lower() for n in _lib.DIODE_PARAMS]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import yalrf_b200
+    from yalrf_b200.Analyses import MultiToneHarmonicBalance
+    y = yalrf_b200.YalRF('x')
+    h = circuits.hb_diode(y)
+    hb = MultiToneHarmonicBalance('HB1', h['freq'], h['K'])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        hb.run(y)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'yalrf_b200')
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dp, f)).read()
+                assert 'oracle' not in src.replace('oracle/', ''), f  # comments may cite the directory only
+                assert 'import oracle' not in src and 'from oracle' not in src
+
+
+def test_netlist_api_matches_reference_semantics():
+    import yalrf_b200
+    y = yalrf_b200.YalRF('Differential Amplifier')
+    h = circuits.diffamp(y)
+    assert y.get_num_nodes() == 11
+    assert y.get_node_idx('gnd') == 0 and y.get_node_idx('nx') == 1 and y.get_node_idx('nvcc') == 2
+    assert len(y.get_nonlinear_devices()) == 4 and len(y.get_linear_devices()) == 11
+    q1, q2 = h['q'][0], h['q'][1]
+    assert q1.options is q2.options                 # shared dict semantics (tests/HB_DiffAmp.py:67-69)
+    c = y.copy()
+    assert c.devices is not y.devices and c.devices[0] is y.devices[0]   # shallow copy (Netlist.py:889-897)
+    assert h['i4'].phase == pytest.approx(np.pi)    # degrees -> radians (CurrentSource.py:12)
+    assert y.get_num_vsources() == 0
+    p = yalrf_b200.Netlist('p')
+    circuits.peltz(p)
+    assert p.get_num_vsources() == 1                # the inductor's DC branch row
+    with pytest.raises(NotImplementedError):
+        y.add_vdc('V1', 'a', 'gnd', 1.0)
+
+
+def test_flatten_and_sweep_arrays():
+    import yalrf_b200
+    from yalrf_b200 import _lib as L
+    from yalrf_b200._flatten import ParamBlock, Topology, dft_tables, source_kinds
+    y = yalrf_b200.YalRF('x')
+    h = circuits.diffamp(y)
+    topo = Topology(y, 1, (10,))
+    assert topo.N == 10 and len(topo.bjts) == 4 and len(topo.src) == 6 and len(topo.lin) == 5
+    kinds = source_kinds(topo, 10e6)
+    assert kinds == [L.SRC_DC, L.SRC_AC1, L.SRC_DC, L.SRC_AC1, L.SRC_DC, L.SRC_DC]
+    with pytest.raises(ValueError):
+        source_kinds(topo, 11e6)
+    pb = ParamBlock(topo, 10e6, 4)
+    pb.set(h['i2'], 'ac', [1., 2., 3., 4.])
+    pb.set(h['q'][0], 'Is', [1e-15, 2e-15, 3e-15, 4e-15])   # shared options dict: applies to all four BJTs
+    pb.finalize()
+    assert pb.src_val.shape == (4, 6, 3)
+    np.testing.assert_allclose(pb.src_val[:, 1, 1], [1, 2, 3, 4])
+    np.testing.assert_allclose(pb.src_val[:, 3, 1], -60e-3)          # I4: phase 180 deg
+    assert abs(pb.src_val[0, 3, 2]) < 1e-16
+    np.testing.assert_allclose(pb.bjt_par[:, :, L.BJT_PARAMS.index('Is')], np.outer([1e-15, 2e-15, 3e-15, 4e-15], np.ones(4)))
+    IDFT, DFT = dft_tables(10)
+    assert np.max(np.abs(DFT @ IDFT - np.eye(21))) < 1e-14
+
+
+def test_dft_tables_match_reference_fixture(golden):
+    from yalrf_b200._flatten import dft_tables
+    g = golden('hb_diode')
+    IDFT, DFT = dft_tables(10)
+    assert np.array_equal(IDFT, g['IDFT'])
+    assert np.array_equal(DFT, g['DFT'])

@@ -1,0 +1,170 @@
+"""MultiToneHarmonicBalance with the reference's surface (yalrf/Analyses/MultiToneHarmonicBalance.py:23-728):
+``run`` / ``run_oscillator`` / ``print_v`` / ``get_v`` / ``convert_to_time`` / ``plot_v`` and the attributes user
+scripts read (``V``, ``Vf``, ``freqs``, ``K``, ``S``, ``N``, ``W``, ``DFT``, ``IDFT``, ``num_tones``).
+
+The Newton loop itself runs on the GPU through libyhb (include/yhb.h); this class only flattens the netlist
+into parameter arrays, calls the C ABI and formats results.  ``run_batch`` / ``run_sweep`` are the batched
+forms the reference expresses as Python ``for`` loops around ``hb.run`` (tests/HB_DiffAmp.py:113-121).
+"""
+import numpy as np
+
+from .. import _engine as E
+from .. import _lib as L
+from .._flatten import ParamBlock
+
+options = dict()
+options['reltol'] = 1e-3
+options['abstol'] = 1e-6
+options['maxiter'] = 100
+
+
+class MultiToneHarmonicBalance:
+
+    def __init__(self, name, freq=1e9, numharmonics=10):
+        self.name = name
+        self.freq = freq
+        self.numharmonics = numharmonics
+        self.options = options.copy()
+        # extensions, off by default = reference behaviour
+        self.pnp_extension = False    # honour BJT polarity in HB (reference: every BJT is NPN, BJT.py:495-503)
+        self.exact_jacobian = False   # re-zero dQdV each iteration (reference accumulates it, :413)
+        self.verbose = False          # print the reference's per-level log lines (:354, :358, :383-384, :597-598)
+        self.last = None              # BatchResult of the last call
+
+    # ------------------------------------------------------------------ helpers
+    def _flags(self):
+        return (L.FLAG_PNP_EXTENSION if self.pnp_extension else 0) | (L.FLAG_EXACT_JACOBIAN if self.exact_jacobian else 0)
+
+    def _setup(self, netlist):
+        self.netlist = netlist.copy()
+        self.lin_devs = self.netlist.get_linear_devices()
+        self.nonlin_devs = self.netlist.get_nonlinear_devices()
+        plan, topo = E.get_plan(self.netlist, self.freq, self.numharmonics, self._flags())
+        self._plan = plan
+        # :247-279
+        if topo.num_tones == 1:
+            self.num_tones = 1
+            self.f1 = self.freq
+        else:
+            self.num_tones = 2
+            self.f1, self.f2 = self.freq
+            self.K1, self.K2 = self.numharmonics
+            self.l0 = self.f1 / (2 * self.K2 + 1)
+        self.K, self.S, self.N, self.W = plan.K, plan.S, plan.N, plan.W
+        self.IDFT, self.DFT = plan.IDFT, plan.DFT
+        return plan, topo
+
+    def _freqs(self, plan):
+        return plan.freqs(self.f1, self.f2 if self.num_tones == 2 else 0.0)
+
+    def get_node_idx(self, node):
+        return self.netlist.get_node_idx(node) - 1
+
+    def _log(self, res, b=0):
+        if not self.verbose:
+            return
+        its = res.level_iters[b]
+        n = int(np.count_nonzero(its))
+        ladder = 0
+        for l in range(n):
+            a = res.level_alpha[b, l]
+            direct = (l == 0 and self._had_v0)
+            if not direct:
+                print('Alpha level: {}'.format(a))
+                ladder += 1
+            print('NR number of iterations: {}'.format(int(its[l])))
+        if ladder:
+            print('Final convergence: {}'.format(bool(res.converged[b])))
+
+    # ------------------------------------------------------------------ solve
+    def run(self, netlist, V0=None):
+        """:234-405.  Returns (converged, freqs, Vf, None, None); failure -> (False, None, None, None, None)."""
+        plan, topo = self._setup(netlist)
+        pb = ParamBlock(topo, self.freq, 1)
+        self._had_v0 = V0 is not None
+        res = E.run_host(plan, pb, self.options, None if V0 is None else np.asarray(V0, dtype=np.float64))
+        self.last = res
+        self._log(res)
+        if not res.converged[0]:
+            return False, None, None, None, None
+        self.freqs = self._freqs(plan)
+        if self.num_tones == 2:
+            self.freqs = np.abs(self.freqs)  # :389-390
+        self.V = res.V[0].reshape(self.W, 1).copy()
+        self.Vf = res.Vf[0].copy()
+        return True, self.freqs, self.Vf, None, None
+
+    def run_batch(self, netlists, V0=None):
+        """Independent solves of netlists sharing one topology (cold starts unless V0[B][W] is given)."""
+        plan, topo = self._setup(netlists[0])
+        blocks = [ParamBlock(topo, self.freq, 1)]
+        key0 = plan
+        for nl in netlists[1:]:
+            p2, t2 = E.get_plan(nl, self.freq, self.numharmonics, self._flags())
+            if p2 is not key0:
+                raise ValueError('run_batch: all netlists must share one topology')
+            blocks.append(ParamBlock(t2, self.freq, 1))
+        pb = ParamBlock.stack(blocks)
+        return self._run_block(plan, pb, V0)
+
+    def run_sweep(self, netlist, sweeps, V0=None, freq=None):
+        """Batched parameter sweep.  ``sweeps`` = [(device, field, values[B]), ...]: ``field`` is an attribute the
+        reference scripts assign between runs (``ac``, ``dc``, ``phase`` [deg], ``R``, ``C``, ``L``, ``alpha``) or a
+        key of ``device.options`` (applied to every device sharing that dict).  ``freq`` (optional [B] or [B][2])
+        sweeps the analysis tone(s); sources and filters at the tone follow it."""
+        plan, topo = self._setup(netlist)
+        B = len(np.asarray(sweeps[0][2])) if sweeps else len(np.asarray(freq))
+        pb = ParamBlock(topo, self.freq, B)
+        for dev, field, values in sweeps:
+            pb.set(dev, field, values)
+        if freq is not None:
+            f = np.asarray(freq, dtype=np.float64)
+            if f.ndim == 1:
+                pb.set_tones(f)
+            else:
+                pb.set_tones(f[:, 0], f[:, 1])
+        return self._run_block(plan, pb, V0)
+
+    def _run_block(self, plan, pb, V0):
+        self._had_v0 = V0 is not None
+        res = E.run_host(plan, pb, self.options, V0)
+        res.freqs = self._freqs(plan)
+        if self.num_tones == 2:
+            res.freqs = np.abs(res.freqs)
+        self.last = res
+        return res
+
+    # ------------------------------------------------------------------ post-processing (:112-135)
+    def print_v(self, node):
+        n = self.get_node_idx(node)
+        print('Voltage at node: ' + node)
+        print('Freq [Hz]\tVmag [V]\tPhase [°]')
+        for k in range(0, self.K + 1):
+            v = self.Vf[n, k]
+            print('{:.2e}\t{:.3e}\t{:.1f}'.format(self.freqs[k], np.abs(v), np.degrees(np.angle(v))))
+
+    def get_v(self, node):
+        n = self.get_node_idx(node)
+        return self.Vf[n]
+
+    def convert_to_time(self, xf):
+        S = 32 * self.K
+        t = 2 / self.freq / S * np.linspace(0, S, S)
+        s = np.arange(S)[:, None]
+        k = np.arange(1, self.K + 1)[None, :]
+        xf = np.asarray(xf)
+        ang = 2. * np.pi * k * s / (S / 2)
+        xt = xf[0].real + (xf[1:].real[None, :] * np.cos(ang) - xf[1:].imag[None, :] * np.sin(ang)).sum(axis=1)
+        return t, xt
+
+    def plot_v(self, node):
+        """:35-110 -- needs matplotlib, which is an optional dependency here."""
+        import matplotlib.pyplot as plt
+        n = self.get_node_idx(node)
+        plt.figure(figsize=(10, 6))
+        plt.title('Frequency-domain $V(j \\omega)$')
+        plt.stem(self.freqs, np.abs(self.Vf[n]), markerfmt='r^', linefmt='r')
+        plt.xlabel('frequency [Hz]')
+        plt.ylabel('V(\'' + node + '\') [V]')
+        plt.grid()
+        plt.tight_layout()

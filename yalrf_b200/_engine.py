@@ -1,0 +1,152 @@
+"""Plan cache and batch solve calls on top of the C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._flatten import ParamBlock, Topology, dft_tables, source_kinds
+
+_plans = {}
+
+
+class Plan:
+    """One compiled topology (yhb_plan) + its grid sizes."""
+
+    def __init__(self, topo, src_kinds, flags, tables=True):
+        lib = L.lib()
+        self.topo = topo
+        self.flags = flags
+        d = L.PlanDesc()
+        d.num_nodes = topo.N
+        d.num_tones = topo.num_tones
+        d.K1 = topo.nh[0]
+        d.K2 = topo.nh[1] if topo.num_tones == 2 else 0
+        keep = []
+
+        def ip(a):
+            a = L.i32(a)
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+        d.num_lin = len(topo.lin)
+        d.lin_kind = ip([k for k, _, _ in topo.lin] or [0])
+        d.lin_nodes = ip([n for _, n, _ in topo.lin] or [[0, 0, 0, 0]])
+        d.num_src = len(topo.src)
+        d.src_kind = ip(src_kinds or [0])
+        d.src_nodes = ip([n for n, _ in topo.src] or [[0, 0]])
+        d.num_diode = len(topo.diodes)
+        d.diode_nodes = ip([n for n, _ in topo.diodes] or [[0, 0]])
+        d.num_bjt = len(topo.bjts)
+        d.bjt_nodes = ip([n for n, _ in topo.bjts] or [[0, 0, 0]])
+        d.num_cubic = len(topo.cubics)
+        d.cubic_nodes = ip([n for n, _ in topo.cubics] or [[0, 0]])
+        d.nl_kind = ip([k for k, _ in topo.nl_order] or [0])
+        d.nl_index = ip([i for _, i in topo.nl_order] or [0])
+        if topo.num_tones == 1:
+            self.K = topo.nh[0]
+        else:
+            self.K = (2 * topo.nh[1] + 1) * topo.nh[0] + topo.nh[1]
+        self.S = 2 * self.K + 1
+        self.N = topo.N
+        self.W = self.S * self.N
+        self.IDFT, self.DFT = dft_tables(self.K)
+        idft, dft = L.f64(self.IDFT), L.f64(self.DFT)
+        d.idft = idft.ctypes.data_as(C.POINTER(C.c_double))
+        d.dft = dft.ctypes.data_as(C.POINTER(C.c_double))
+        d.flags = flags
+        h = C.c_void_p()
+        L.check(lib.yhb_plan_create(C.byref(d), C.byref(h)))
+        self.handle = h
+
+    def freqs(self, f1, f2=0.0):
+        out = np.zeros(self.K + 1)
+        L.check(L.lib().yhb_plan_freqs(self.handle, float(f1), float(f2), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().yhb_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def get_plan(netlist, freq, numharmonics, flags=0, match_tones=True):
+    """(plan, topology) for this netlist shape and tone grid; plans are cached by topology."""
+    if isinstance(freq, float):
+        num_tones, nh = 1, (int(numharmonics),)
+    elif isinstance(freq, list) and len(freq) == 2:
+        num_tones, nh = 2, (int(numharmonics[0]), int(numharmonics[1]))
+    else:  # MultiToneHarmonicBalance.py:247-275 (ints fall through to the error print there)
+        raise ValueError('ERROR: only one and two-tones are currently supported (freq must be a float or a list '
+                         'of two floats)')
+    topo = Topology(netlist, num_tones, nh)
+    kinds = source_kinds(topo, freq, match_tones)
+    key = topo.key(kinds, flags)
+    plan = _plans.get(key)
+    if plan is None:
+        plan = Plan(topo, kinds, flags)
+        _plans[key] = plan
+    return plan, topo
+
+
+class BatchResult:
+    """Results of a batched solve (numpy, host)."""
+
+    def __init__(self, plan, B):
+        self.B = B
+        self.V = np.zeros((B, plan.W))
+        self.Vf = np.zeros((B, plan.N, plan.K + 1), dtype=np.complex128)
+        self.converged = np.zeros(B, dtype=np.int32)
+        self.newton_iters = np.zeros(B, dtype=np.int32)
+        self.lu_count = np.zeros(B, dtype=np.int32)
+        self.level_iters = np.zeros((B, L.MAX_LEVELS), dtype=np.int32)
+        self.level_alpha = np.zeros((B, L.MAX_LEVELS))
+        self.err = np.zeros(B)
+
+    def levels(self, b=0):
+        it = self.level_iters[b]
+        return it[it > 0].tolist()
+
+
+def make_params(pb):
+    p = L.Params()
+    p.batch = pb.B
+    p.tones = L.ptr(pb.tones)
+    p.lin_val = L.ptr(pb.lin_val)
+    p.src_val = L.ptr(pb.src_val)
+    p.diode_par = L.ptr(pb.diode_par)
+    p.bjt_par = L.ptr(pb.bjt_par)
+    p.cubic_par = L.ptr(pb.cubic_par)
+    return p
+
+
+def make_options(options):
+    o = L.Options()
+    o.reltol = float(options['reltol'])
+    o.abstol = float(options['abstol'])
+    o.maxiter = int(options['maxiter'])
+    return o
+
+
+def run_host(plan, pb, options, V0=None):
+    """run() for a batch through yhb_run_host: host arrays in, host arrays out (H2D / D2H inside)."""
+    pb.finalize()
+    res = BatchResult(plan, pb.B)
+    r = L.Result()
+    r.V = L.ptr(res.V)
+    r.Vf = L.ptr(res.Vf)
+    r.converged = L.ptr(res.converged)
+    r.newton_iters = L.ptr(res.newton_iters)
+    r.lu_count = L.ptr(res.lu_count)
+    r.level_iters = L.ptr(res.level_iters)
+    r.level_alpha = L.ptr(res.level_alpha)
+    r.err = L.ptr(res.err)
+    p = make_params(pb)
+    o = make_options(options)
+    v0 = None
+    if V0 is not None:
+        v0 = L.f64(np.asarray(V0).reshape(pb.B, plan.W))
+    L.check(L.lib().yhb_run_host(plan.handle, C.byref(p), C.byref(o), L.ptr(v0), C.byref(r)))
+    return res

@@ -1,0 +1,115 @@
+"""ctypes binding of libyhb.so (include/yhb.h).  There is no fallback: a missing library is an error."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libyhb.so')
+
+# enums of include/yhb.h
+LIN_RESISTOR, LIN_CAPACITOR, LIN_INDUCTOR, LIN_GYRATOR, LIN_IHF = range(5)
+SRC_DC, SRC_AC1, SRC_AC2, SRC_DC_ONLY = range(4)
+DIODE_PARAMS = ['Temp', 'Is', 'N', 'Isr', 'Nr', 'Ikf', 'Bv', 'Ibv', 'Rs', 'Area']
+BJT_PARAMS = ['Temp', 'Is', 'Nf', 'Nr', 'Ikf', 'Ikr', 'Vaf', 'Var', 'Ise', 'Ne', 'Isc', 'Nc', 'Bf', 'Br',
+              'Cje', 'Vje', 'Mje', 'Cjc', 'Vjc', 'Mjc', 'Xcjc', 'Cjs', 'Vjs', 'Mjs', 'Fc', 'Tf', 'Xtf', 'Vtf',
+              'Itf', 'Tr', 'Area', 'type']
+DIODE_NPAR = len(DIODE_PARAMS)
+BJT_NPAR = len(BJT_PARAMS)
+FLAG_PNP_EXTENSION = 1
+FLAG_EXACT_JACOBIAN = 2
+MAX_LEVELS = 64
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [('num_nodes', C.c_int32), ('num_tones', C.c_int32), ('K1', C.c_int32), ('K2', C.c_int32),
+                ('num_lin', C.c_int32), ('lin_kind', _i32p), ('lin_nodes', _i32p),
+                ('num_src', C.c_int32), ('src_kind', _i32p), ('src_nodes', _i32p),
+                ('num_diode', C.c_int32), ('diode_nodes', _i32p),
+                ('num_bjt', C.c_int32), ('bjt_nodes', _i32p),
+                ('num_cubic', C.c_int32), ('cubic_nodes', _i32p),
+                ('nl_kind', _i32p), ('nl_index', _i32p),
+                ('idft', _f64p), ('dft', _f64p), ('flags', C.c_int32)]
+
+
+class Params(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('tones', C.c_void_p), ('lin_val', C.c_void_p), ('src_val', C.c_void_p),
+                ('diode_par', C.c_void_p), ('bjt_par', C.c_void_p), ('cubic_par', C.c_void_p)]
+
+
+class Options(C.Structure):
+    _fields_ = [('reltol', C.c_double), ('abstol', C.c_double), ('maxiter', C.c_int32), ('reserved', C.c_int32)]
+
+
+class Result(C.Structure):
+    _fields_ = [('V', C.c_void_p), ('Vf', C.c_void_p), ('converged', C.c_void_p), ('newton_iters', C.c_void_p),
+                ('lu_count', C.c_void_p), ('level_iters', C.c_void_p), ('level_alpha', C.c_void_p),
+                ('err', C.c_void_p)]
+
+
+_lib = None
+
+EXPORTS = ['yhb_last_error', 'yhb_version', 'yhb_set_device', 'yhb_plan_create', 'yhb_plan_destroy',
+           'yhb_plan_dims', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_newton',
+           'yhb_run_host', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu']
+
+
+def lib():
+    """Load libyhb.so once.  Raises if it was not built (run __graft_entry__.build() or csrc/build.sh)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError('yalrf_b200: %s is missing -- build it with yalrf_b200/csrc/build.sh; there is no '
+                           'CPU fallback' % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.yhb_last_error.restype = C.c_char_p
+    L.yhb_version.restype = C.c_int
+    L.yhb_set_device.argtypes = [C.c_int32]
+    L.yhb_plan_create.argtypes = [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]
+    L.yhb_plan_destroy.argtypes = [C.c_void_p]
+    L.yhb_plan_destroy.restype = None
+    L.yhb_plan_dims.argtypes = [C.c_void_p, _i32p, _i32p, _i32p, _i32p]
+    L.yhb_plan_freqs.argtypes = [C.c_void_p, C.c_double, C.c_double, _f64p]
+    L.yhb_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
+    L.yhb_workspace_bytes.restype = C.c_size_t
+    L.yhb_dc_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                               C.c_void_p]
+    L.yhb_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.c_void_p, C.c_size_t, C.c_int32,
+                            C.c_void_p, C.POINTER(Result), C.c_void_p]
+    L.yhb_newton.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.c_void_p, C.c_size_t,
+                             C.c_void_p, C.POINTER(Result), C.c_void_p]
+    L.yhb_run_host.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.c_void_p, C.POINTER(Result)]
+    L.yhb_stage_ifft.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.yhb_stage_device_eval.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    L.yhb_stage_assemble.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.yhb_stage_lu.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('libyhb error %d: %s' % (rc, lib().yhb_last_error().decode()))
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a):
+    """raw address of a numpy array / torch tensor (or None)"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()

@@ -1,0 +1,788 @@
+// libyhb.so -- C ABI (include/yhb.h) over the staged harmonic-balance kernels.
+// Host side: plan compilation (stamp tables), workspace carving, and the launch loop that plays
+// run() / hb_loop (yalrf/Analyses/MultiToneHarmonicBalance.py:234-631) for a whole batch.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "yhb_dc.cuh"
+#include "yhb_kernels.cuh"
+
+namespace yhb {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+#define YHB_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                     \
+            return -2;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+template <typename T>
+static const T *upload(Plan *pl, const std::vector<T> &v) {
+    void *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    if (!v.empty()) cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    pl->allocs.push_back(d);
+    return reinterpret_cast<const T *>(d);
+}
+
+struct TermList {
+    std::vector<std::vector<Term>> rows;
+    void add(int row, int idx, int sgn) {
+        if ((int)rows.size() <= row) rows.resize(row + 1);
+        rows[row].push_back(Term{idx, sgn});
+    }
+    void flatten(int nrows, std::vector<int> &ptr, std::vector<Term> &out) const {
+        ptr.assign(nrows + 1, 0);
+        out.clear();
+        for (int r = 0; r < nrows; ++r) {
+            if (r < (int)rows.size()) out.insert(out.end(), rows[r].begin(), rows[r].end());
+            ptr[r + 1] = (int)out.size();
+        }
+    }
+};
+
+}  // namespace yhb
+
+using namespace yhb;
+
+struct yhb_plan : public yhb::Plan {
+    std::vector<int> nl_kind, nl_index;
+    const int *nl_kind_dev, *nl_index_dev;
+    int *pinned_counts;
+    cudaStream_t own_stream;
+    // yhb_run_host buffers
+    void *hbuf;
+    size_t hbuf_bytes;
+    std::mutex mu;
+};
+
+extern "C" const char *yhb_last_error(void) { return g_err.c_str(); }
+extern "C" int yhb_version(void) { return YHB_VERSION; }
+extern "C" int yhb_set_device(int32_t device) {
+    YHB_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
+    if (!desc || !out) { set_error("null argument"); return -1; }
+    if (desc->num_nodes < 1 || (desc->num_tones != 1 && desc->num_tones != 2) || desc->K1 < 1 ||
+        (desc->num_tones == 2 && desc->K2 < 1)) {
+        set_error("bad plan descriptor: need N >= 1, one or two tones, K >= 1");
+        return -1;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: libyhb has no CPU fallback");
+        return -3;
+    }
+    yhb_plan *pl = new (std::nothrow) yhb_plan();
+    if (!pl) { set_error("out of memory"); return -1; }
+    PlanDev &d = pl->d;
+    const int N = desc->num_nodes;
+    d.N = N;
+    d.ntones = desc->num_tones;
+    d.K2 = desc->num_tones == 2 ? desc->K2 : 0;
+    if (desc->num_tones == 1) {  // :247-251
+        d.K = desc->K1;
+        for (int k = 0; k <= d.K; ++k) { pl->bin_k1.push_back(k); pl->bin_k2.push_back(0); }
+    } else {  // :252-273
+        d.K = (2 * desc->K2 + 1) * desc->K1 + desc->K2;
+        for (int k1 = 0; k1 <= desc->K1; ++k1)
+            for (int k2 = -desc->K2; k2 <= desc->K2; ++k2) {
+                if (k1 == 0 && k2 < 0) continue;
+                pl->bin_k1.push_back(k1);
+                pl->bin_k2.push_back(k2);
+            }
+    }
+    d.S = 2 * d.K + 1;
+    d.W = d.S * N;
+    d.nlin = desc->num_lin;
+    d.nsrc = desc->num_src;
+    d.nd = desc->num_diode;
+    d.nb = desc->num_bjt;
+    d.nc = desc->num_cubic;
+    d.flags = desc->flags;
+    const int S = d.S, K = d.K;
+
+    auto check_nodes = [&](const int32_t *a, int cnt) {
+        for (int i = 0; i < cnt; ++i)
+            if (a[i] < 0 || a[i] > N) return false;
+        return true;
+    };
+    if (!check_nodes(desc->lin_nodes, 4 * d.nlin) || !check_nodes(desc->src_nodes, 2 * d.nsrc) ||
+        !check_nodes(desc->diode_nodes, 2 * d.nd) || !check_nodes(desc->bjt_nodes, 3 * d.nb) ||
+        !check_nodes(desc->cubic_nodes, 2 * d.nc)) {
+        set_error("node index out of range");
+        delete pl;
+        return -1;
+    }
+    pl->lin_kind.assign(desc->lin_kind, desc->lin_kind + d.nlin);
+    pl->lin_nodes.assign(desc->lin_nodes, desc->lin_nodes + 4 * d.nlin);
+    pl->src_kind.assign(desc->src_kind, desc->src_kind + d.nsrc);
+    pl->src_nodes.assign(desc->src_nodes, desc->src_nodes + 2 * d.nsrc);
+    pl->diode_nodes.assign(desc->diode_nodes, desc->diode_nodes + 2 * d.nd);
+    pl->bjt_nodes.assign(desc->bjt_nodes, desc->bjt_nodes + 3 * d.nb);
+    pl->cubic_nodes.assign(desc->cubic_nodes, desc->cubic_nodes + 2 * d.nc);
+    pl->num_inductors = 0;
+    for (int e = 0; e < d.nlin; ++e) pl->num_inductors += pl->lin_kind[e] == YHB_LIN_INDUCTOR;
+
+    // nonlinear devices in netlist order (kind 0 diode, 1 bjt, 2 cubic)
+    const int nnl = d.nd + d.nb + d.nc;
+    if (desc->nl_kind && desc->nl_index) {
+        pl->nl_kind.assign(desc->nl_kind, desc->nl_kind + nnl);
+        pl->nl_index.assign(desc->nl_index, desc->nl_index + nnl);
+    } else {
+        for (int i = 0; i < d.nd; ++i) { pl->nl_kind.push_back(0); pl->nl_index.push_back(i); }
+        for (int i = 0; i < d.nc; ++i) { pl->nl_kind.push_back(2); pl->nl_index.push_back(i); }
+        for (int i = 0; i < d.nb; ++i) { pl->nl_kind.push_back(1); pl->nl_index.push_back(i); }
+    }
+
+    // waveform slots: device order inside the evaluation kernel is diodes, cubics, bjts
+    std::vector<int> wave_base;
+    int nw = 0;
+    for (int i = 0; i < d.nd; ++i) { wave_base.push_back(nw); nw += 2; }
+    for (int i = 0; i < d.nc; ++i) { wave_base.push_back(nw); nw += 2; }
+    for (int i = 0; i < d.nb; ++i) { wave_base.push_back(nw); nw += kBjtWaves; }
+    d.nwave = nw;
+
+    // ---- J block structure and stamp lists (:459-475 diode/cubic, :524-570 BJT), netlist order
+    std::map<std::pair<int, int>, int> pair_id;
+    std::vector<std::pair<int, int>> pairs;
+    auto get_pair = [&](int n, int m) {  // reference node numbers, both > 0
+        auto key = std::make_pair(n - 1, m - 1);
+        auto it = pair_id.find(key);
+        if (it != pair_id.end()) return it->second;
+        int id = (int)pairs.size();
+        pair_id[key] = id;
+        pairs.push_back(key);
+        return id;
+    };
+    TermList pg, pc, ni, nq, ns, plin;
+    auto g_stamp = [&](int n, int m, int wave, int sgn) { if (n > 0 && m > 0) pg.add(get_pair(n, m), wave, sgn); };
+    auto c_stamp = [&](int n, int m, int slot, int sgn) { if (n > 0 && m > 0) pc.add(get_pair(n, m), slot, sgn); };
+    for (int t = 0; t < nnl; ++t) {
+        int kind = pl->nl_kind[t], i = pl->nl_index[t];
+        if (kind == 0 || kind == 2) {
+            const int *nd = kind == 0 ? &pl->diode_nodes[2 * i] : &pl->cubic_nodes[2 * i];
+            int wb = wave_base[kind == 0 ? i : d.nd + i];
+            int n1 = nd[0], n2 = nd[1];
+            g_stamp(n1, n1, wb, +1);
+            if (n1 > 0) ni.add(n1 - 1, wb + 1, +1);
+            g_stamp(n2, n2, wb, +1);
+            if (n2 > 0) ni.add(n2 - 1, wb + 1, -1);
+            g_stamp(n1, n2, wb, -1);
+            g_stamp(n2, n1, wb, -1);
+        } else {
+            const int *nd = &pl->bjt_nodes[3 * i];
+            int wb = wave_base[d.nd + d.nc + i];
+            int B = nd[0], C = nd[1], E = nd[2];
+            const int Ib = wb, Ic = wb + 1, Ie = wb + 2, Qbe = wb + 3, Qbc = wb + 4, Qsc = wb + 5;
+            const int gmu = wb + 6, gpi = wb + 7, gmf = wb + 8, gmr = wb + 9;
+            const int Cbc = 4 * i, Cbe = 4 * i + 1, Cbebc = 4 * i + 2, Csc = 4 * i + 3;
+            // :524-530
+            g_stamp(B, B, gmu, +1); g_stamp(B, B, gpi, +1);
+            c_stamp(B, B, Cbc, +1); c_stamp(B, B, Cbe, +1); c_stamp(B, B, Cbebc, +1);
+            if (B > 0) { ni.add(B - 1, Ib, +1); nq.add(B - 1, Qbe, +1); nq.add(B - 1, Qbc, +1); }
+            // :532-538
+            g_stamp(B, C, gmu, -1);
+            g_stamp(C, B, gmu, -1); g_stamp(C, B, gmf, +1); g_stamp(C, B, gmr, +1);
+            c_stamp(B, C, Cbc, -1); c_stamp(B, C, Cbebc, -1);
+            c_stamp(C, B, Cbc, -1);
+            // :540-546
+            g_stamp(B, E, gpi, -1);
+            g_stamp(E, B, gpi, -1); g_stamp(E, B, gmf, -1); g_stamp(E, B, gmr, -1);
+            c_stamp(B, E, Cbe, -1);
+            c_stamp(E, B, Cbe, -1); c_stamp(E, B, Cbebc, -1);
+            // :548-554
+            g_stamp(C, C, gmu, +1); g_stamp(C, C, gmr, -1);
+            c_stamp(C, C, Cbc, +1); c_stamp(C, C, Csc, +1);
+            if (C > 0) { ni.add(C - 1, Ic, +1); nq.add(C - 1, Qbc, -1); nq.add(C - 1, Qsc, +1); }
+            // :556-562
+            g_stamp(C, E, gmf, -1);
+            g_stamp(E, C, gmr, +1);
+            c_stamp(E, C, Cbebc, +1);
+            // :564-570
+            g_stamp(E, E, gpi, +1); g_stamp(E, E, gmf, +1);
+            c_stamp(E, E, Cbe, +1);
+            if (E > 0) { ni.add(E - 1, Ie, -1); nq.add(E - 1, Qbe, -1); }
+        }
+    }
+    d.npair_nl = (int)pairs.size();
+    // linear stamps (add_mthb_stamps of each linear class), netlist order
+    auto l_stamp = [&](int n, int m, int e, int sgn) { if (n > 0 && m > 0) plin.add(get_pair(n, m), e, sgn); };
+    for (int e = 0; e < d.nlin; ++e) {
+        const int *nd = &pl->lin_nodes[4 * e];
+        if (pl->lin_kind[e] == YHB_LIN_GYRATOR) {  // Gyrator.py:45-73
+            l_stamp(nd[0], nd[1], e, +1); l_stamp(nd[1], nd[0], e, -1);
+            l_stamp(nd[0], nd[2], e, -1); l_stamp(nd[2], nd[0], e, +1);
+            l_stamp(nd[1], nd[3], e, +1); l_stamp(nd[3], nd[1], e, -1);
+            l_stamp(nd[2], nd[3], e, -1); l_stamp(nd[3], nd[2], e, +1);
+        } else {
+            l_stamp(nd[0], nd[0], e, +1);
+            l_stamp(nd[1], nd[1], e, +1);
+            l_stamp(nd[0], nd[1], e, -1);
+            l_stamp(nd[1], nd[0], e, -1);
+        }
+    }
+    d.npair = (int)pairs.size();
+    for (int s = 0; s < d.nsrc; ++s) {
+        int n1 = pl->src_nodes[2 * s], n2 = pl->src_nodes[2 * s + 1];
+        if (n1 > 0) ns.add(n1 - 1, s, +1);
+        if (n2 > 0) ns.add(n2 - 1, s, -1);
+    }
+
+    std::vector<int> pair_n, pair_m, pair_of((size_t)N * N, -1);
+    for (int p = 0; p < d.npair; ++p) {
+        pair_n.push_back(pairs[p].first);
+        pair_m.push_back(pairs[p].second);
+        pair_of[(size_t)pairs[p].first * N + pairs[p].second] = p;
+    }
+    std::vector<int> row_ptr(N + 1, 0), row_pairs;
+    for (int n = 0; n < N; ++n) {
+        for (int m = 0; m < N; ++m)
+            if (pair_of[(size_t)n * N + m] >= 0) row_pairs.push_back(pair_of[(size_t)n * N + m]);
+        row_ptr[n + 1] = (int)row_pairs.size();
+    }
+    std::vector<int> ptr;
+    std::vector<Term> terms;
+
+    // DFT tables: caller's (reference-identical numpy tables) or analytic (:294-302)
+    std::vector<double> idft((size_t)S * S), dft((size_t)S * S);
+    if (desc->idft && desc->dft) {
+        std::copy(desc->idft, desc->idft + (size_t)S * S, idft.begin());
+        std::copy(desc->dft, desc->dft + (size_t)S * S, dft.begin());
+    } else {
+        const double pi = 3.141592653589793;
+        for (int s = 0; s < S; ++s) {
+            idft[(size_t)s * S] = 1.0;
+            dft[s] = 1.0 / S;
+            for (int k = 1; k <= K; ++k) {
+                double ang = 2 * pi * (double)(((long long)k * s) % S) / S;
+                idft[(size_t)s * S + 2 * k - 1] = std::cos(ang);
+                idft[(size_t)s * S + 2 * k] = std::sin(ang);
+                dft[(size_t)(2 * k - 1) * S + s] = 2.0 / S * std::cos(ang);
+                dft[(size_t)(2 * k) * S + s] = 2.0 / S * std::sin(ang);
+            }
+        }
+    }
+
+    bool ok = true;
+#define UP(field, vec) do { d.field = upload(pl, vec); ok = ok && d.field; } while (0)
+    UP(idft, idft);
+    UP(dft, dft);
+    UP(bin_k1, pl->bin_k1);
+    UP(bin_k2, pl->bin_k2);
+    UP(lin_kind, pl->lin_kind);
+    UP(src_kind, pl->src_kind);
+    UP(src_nodes, pl->src_nodes);
+    UP(diode_nodes, pl->diode_nodes);
+    UP(bjt_nodes, pl->bjt_nodes);
+    UP(cubic_nodes, pl->cubic_nodes);
+    UP(dev_wave_base, wave_base);
+    UP(pair_n, pair_n);
+    UP(pair_m, pair_m);
+    UP(pair_of, pair_of);
+    UP(row_ptr, row_ptr);
+    UP(row_pairs, row_pairs);
+    plin.flatten(d.npair, ptr, terms); UP(plin_ptr, ptr); UP(plin, terms);
+    pg.flatten(d.npair_nl, ptr, terms); UP(pg_ptr, ptr); UP(pg, terms);
+    pc.flatten(d.npair_nl, ptr, terms); UP(pc_ptr, ptr); UP(pc, terms);
+    ni.flatten(N, ptr, terms); UP(ni_ptr, ptr); UP(ni, terms);
+    nq.flatten(N, ptr, terms); UP(nq_ptr, ptr); UP(nq, terms);
+    ns.flatten(N, ptr, terms); UP(ns_ptr, ptr); UP(ns, terms);
+#undef UP
+    pl->lin_nodes_dev = upload(pl, pl->lin_nodes);
+    pl->nl_kind_dev = upload(pl, pl->nl_kind);
+    pl->nl_index_dev = upload(pl, pl->nl_index);
+    ok = ok && pl->lin_nodes_dev && pl->nl_kind_dev && pl->nl_index_dev;
+    pl->pinned_counts = nullptr;
+    pl->own_stream = nullptr;
+    pl->hbuf = nullptr;
+    pl->hbuf_bytes = 0;
+    if (ok) ok = cudaHostAlloc((void **)&pl->pinned_counts, 4 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        set_error(std::string("plan upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+        yhb_plan_destroy(pl);
+        return -2;
+    }
+    *out = pl;
+    return 0;
+}
+
+extern "C" void yhb_plan_destroy(yhb_plan *pl) {
+    if (!pl) return;
+    for (void *p : pl->allocs) cudaFree(p);
+    if (pl->pinned_counts) cudaFreeHost(pl->pinned_counts);
+    if (pl->hbuf) cudaFree(pl->hbuf);
+    if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+    delete pl;
+}
+
+extern "C" int yhb_plan_dims(const yhb_plan *pl, int32_t *N, int32_t *K, int32_t *S, int32_t *W) {
+    if (!pl) { set_error("null plan"); return -1; }
+    if (N) *N = pl->d.N;
+    if (K) *K = pl->d.K;
+    if (S) *S = pl->d.S;
+    if (W) *W = pl->d.W;
+    return 0;
+}
+
+extern "C" int yhb_plan_freqs(const yhb_plan *pl, double f1, double f2, double *freqs) {
+    if (!pl || !freqs) { set_error("null argument"); return -1; }
+    for (int k = 0; k <= pl->d.K; ++k)
+        freqs[k] = pl->d.ntones == 1 ? f1 * (double)k : (double)pl->bin_k1[k] * f1 + (double)pl->bin_k2[k] * f2;
+    return 0;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------
+namespace {
+
+struct Carver {
+    char *base;
+    size_t off;
+    template <typename T>
+    T *take(size_t count) {
+        off = align_up(off);
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+constexpr size_t kMaxEvalSmem = 200 * 1024;
+
+struct Layout {
+    Workspace ws;
+    DiodeDerived *dd;
+    BjtDerived *bd;
+    size_t bytes;
+    bool eval_smem;
+};
+
+Layout carve(const yhb_plan *pl, int B, void *base) {
+    const PlanDev &d = pl->d;
+    Layout L;
+    Carver c{reinterpret_cast<char *>(base), 0};
+    Workspace &ws = L.ws;
+    const size_t W = d.W, S = d.S, K1 = d.K + 1;
+    ws.batch = B;
+    ws.stage_first = 1;
+    ws.ctl = c.take<Ctl>(B);
+    ws.V = c.take<double>(B * W);
+    ws.Vlevel = c.take<double>(B * W);
+    ws.dV = c.take<double>(B * W);
+    ws.vtprev = c.take<double>(B * W);
+    ws.F = c.take<double>(B * W);
+    ws.cacc = c.take<double>((size_t)B * std::max(d.nb, 1) * 4 * S);
+    ws.spec = c.take<double>((size_t)B * std::max(d.npair_nl, 1) * 4 * S);
+    ws.ylin = c.take<double>((size_t)B * d.npair * K1 * 2);
+    ws.omega = c.take<double>(B * K1);
+    ws.negbin = c.take<int>(B * K1);
+    ws.Is = c.take<double>(B * W);
+    const size_t esd = eval_scratch_doubles(d);
+    L.eval_smem = esd * sizeof(double) <= kMaxEvalSmem;
+    ws.scratch_stride = L.eval_smem ? 0 : esd;
+    ws.scratch = c.take<double>(L.eval_smem ? 1 : (size_t)B * esd);
+    ws.J = c.take<double>((size_t)B * W * W);
+    ws.list[0] = c.take<int>(B);
+    ws.list[1] = c.take<int>(B);
+    ws.count = c.take<int>(4);
+    ws.level_iters = c.take<int32_t>((size_t)B * YHB_MAX_LEVELS);
+    ws.level_alpha = c.take<double>((size_t)B * YHB_MAX_LEVELS);
+    ws.dcV = c.take<double>((size_t)B * d.N);
+    ws.dcinfo = c.take<int>(2 * (size_t)B);
+    const int M = d.N + pl->num_inductors;
+    ws.dc_stride = dc_scratch_doubles(M, d.nd, d.nb);
+    ws.dcscratch = c.take<double>((size_t)B * ws.dc_stride);
+    L.dd = c.take<DiodeDerived>((size_t)B * std::max(d.nd, 1));
+    L.bd = c.take<BjtDerived>((size_t)B * std::max(d.nb, 1));
+    L.bytes = align_up(c.off);
+    return L;
+}
+
+int check_params(const yhb_plan *pl, const yhb_params *p) {
+    if (!pl || !p) { set_error("null argument"); return -1; }
+    if (p->batch < 1) { set_error("batch must be >= 1"); return -1; }
+    const PlanDev &d = pl->d;
+    if (!p->tones || (d.nlin && !p->lin_val) || (d.nsrc && !p->src_val) || (d.nd && !p->diode_par) ||
+        (d.nb && !p->bjt_par) || (d.nc && !p->cubic_par)) {
+        set_error("missing parameter array");
+        return -1;
+    }
+    return 0;
+}
+
+int launch_prepare(const yhb_plan *pl, const yhb_params *p, const Layout &L, cudaStream_t st) {
+    PrepArgs a;
+    a.tones = p->tones;
+    a.lin_val = p->lin_val;
+    a.src_val = p->src_val;
+    a.diode_par = p->diode_par;
+    a.bjt_par = p->bjt_par;
+    a.omega = L.ws.omega;
+    a.ylin = L.ws.ylin;
+    a.Is = L.ws.Is;
+    a.negbin = L.ws.negbin;
+    a.dd = L.dd;
+    a.bd = L.bd;
+    k_prepare<<<p->batch, 128, 0, st>>>(pl->d, a, p->batch);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+EvalArgs eval_args(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, const Layout &L) {
+    EvalArgs e;
+    memset(&e, 0, sizeof(e));
+    e.cubic_par = p->cubic_par;
+    e.dd = L.dd;
+    e.bd = L.bd;
+    e.reltol = opt ? opt->reltol : 1e-3;
+    e.abstol = opt ? opt->abstol : 1e-6;
+    e.maxiter = opt ? opt->maxiter : 100;
+    e.use_smem = L.eval_smem;
+    return e;
+}
+
+int eval_smem_bytes(const yhb_plan *pl, const Layout &L) {
+    return L.eval_smem ? (int)(eval_scratch_doubles(pl->d) * sizeof(double)) : 0;
+}
+
+int ensure_eval_attr(int bytes) {
+    static int configured = 0;
+    if (bytes > configured) {
+        YHB_CUDA(cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxEvalSmem));
+        configured = (int)kMaxEvalSmem;
+    }
+    return 0;
+}
+
+// the Newton / continuation launch loop shared by yhb_solve and yhb_newton
+int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, Layout &L, int have_v0,
+             const double *alpha_fixed, const yhb_result *res, cudaStream_t st) {
+    const PlanDev &d = pl->d;
+    const int B = p->batch;
+    Workspace &ws = L.ws;
+    if (int rc = launch_prepare(pl, p, L, st)) return rc;
+    k_init<<<B, 128, 0, st>>>(d, ws, have_v0, alpha_fixed);
+    YHB_CUDA(cudaGetLastError());
+    EvalArgs ea = eval_args(pl, p, opt, L);
+    const int smem = eval_smem_bytes(pl, L);
+    if (int rc = ensure_eval_attr(smem)) return rc;
+    int cur = 0, nactive = B;
+    int *hc = pl->pinned_counts;
+    long rounds = 0;
+    while (nactive > 0) {
+        YHB_CUDA(cudaMemsetAsync(ws.count + (cur ^ 1), 0, sizeof(int), st));
+        ea.cur = cur;
+        k_eval<<<nactive, kEvalThreads, smem, st>>>(d, ws, ea);
+        YHB_CUDA(cudaGetLastError());
+        YHB_CUDA(cudaMemcpyAsync(hc, ws.count, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        YHB_CUDA(cudaStreamSynchronize(st));
+        const int nsolve = hc[cur ^ 1];
+        if (nsolve > 0) {
+            dim3 ga(nsolve, (d.W + kAsmRows - 1) / kAsmRows);
+            k_assemble<<<ga, 256, 0, st>>>(d, ws, cur ^ 1, 0);
+            k_lu<<<nsolve, kLuThreads, (d.W + 1) * sizeof(double), st>>>(d, ws, cur ^ 1);
+            YHB_CUDA(cudaGetLastError());
+        }
+        nactive = nsolve;
+        cur ^= 1;
+        if (++rounds > 100000) { set_error("Newton launch loop did not terminate"); return -4; }
+    }
+    FinishArgs fa;
+    fa.Vf = res->Vf;
+    fa.converged = res->converged;
+    fa.newton_iters = res->newton_iters;
+    fa.lu_count = res->lu_count;
+    fa.level_iters = res->level_iters;
+    fa.level_alpha = res->level_alpha;
+    fa.err = res->err;
+    k_finish<<<B, 128, 0, st>>>(d, ws, fa);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" size_t yhb_workspace_bytes(const yhb_plan *pl, int32_t batch) {
+    if (!pl || batch < 1) return 0;
+    return carve(pl, batch, nullptr).bytes;
+}
+
+extern "C" int yhb_dc_solve(const yhb_plan *pl, const yhb_params *p, void *wsbuf, size_t ws_bytes, double *Vdc,
+                            int32_t *dc_info, void *stream) {
+    if (int rc = check_params(pl, p)) return rc;
+    Layout L = carve(pl, p->batch, wsbuf);
+    if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
+    const PlanDev &d = pl->d;
+    DcArgs a;
+    a.lin_val = p->lin_val;
+    a.src_val = p->src_val;
+    a.diode_par = p->diode_par;
+    a.bjt_par = p->bjt_par;
+    a.cubic_par = p->cubic_par;
+    a.lin_nodes = pl->lin_nodes_dev;
+    a.nl_kind = pl->nl_kind_dev;
+    a.nl_index = pl->nl_index_dev;
+    a.nnl = d.nd + d.nb + d.nc;
+    a.M = d.N + pl->num_inductors;
+    a.scratch = L.ws.dcscratch;
+    a.stride = L.ws.dc_stride;
+    a.Vdc = Vdc ? Vdc : L.ws.dcV;
+    a.info = dc_info ? dc_info : L.ws.dcinfo;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_dc<<<p->batch, kDcThreads, (a.M + 2) * sizeof(double), st>>>(d, a, p->batch);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int solve_common(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
+                        size_t ws_bytes, int have_v0, const double *Vdc, const double *alpha,
+                        const yhb_result *res, void *stream) {
+    if (int rc = check_params(pl, p)) return rc;
+    if (!res) { set_error("null result"); return -1; }
+    Layout L = carve(pl, p->batch, wsbuf);
+    if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
+    if (have_v0 && !res->V) { set_error("have_v0 set but res->V is null"); return -1; }
+    if (!have_v0 && !Vdc && !alpha) { set_error("cold start needs Vdc"); return -1; }
+    if (res->V) L.ws.V = res->V;
+    if (Vdc) L.ws.dcV = const_cast<double *>(Vdc);
+    std::lock_guard<std::mutex> lk(const_cast<yhb_plan *>(pl)->mu);  // pinned counter buffer is per plan
+    return run_loop(pl, p, opt, L, have_v0, alpha, res, (cudaStream_t)stream);
+}
+
+extern "C" int yhb_solve(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
+                         size_t ws_bytes, int32_t have_v0, const double *Vdc, const yhb_result *res, void *stream) {
+    return solve_common(pl, p, opt, wsbuf, ws_bytes, have_v0, Vdc, nullptr, res, stream);
+}
+
+extern "C" int yhb_newton(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
+                          size_t ws_bytes, const double *alpha, const yhb_result *res, void *stream) {
+    if (!alpha) { set_error("null alpha"); return -1; }
+    return solve_common(pl, p, opt, wsbuf, ws_bytes, 1, nullptr, alpha, res, stream);
+}
+
+// ---- end-to-end entry with host buffers -----------------------------------------------------------
+extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb_options *opt, const double *V0,
+                            const yhb_result *hr) {
+    yhb_plan *pl = const_cast<yhb_plan *>(cpl);
+    if (int rc = check_params(pl, hp)) return rc;
+    if (!hr) { set_error("null result"); return -1; }
+    const PlanDev &d = pl->d;
+    const size_t B = hp->batch, W = d.W, K1 = d.K + 1;
+    if (!pl->own_stream) YHB_CUDA(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
+    cudaStream_t st = pl->own_stream;
+    // device staging: parameters + results + workspace, one allocation cached on the plan
+    Carver c{nullptr, 0};
+    auto plan_bytes = [&](Carver &cv, yhb_params &dp, yhb_result &dr, void *&wsb, size_t wsbytes) {
+        dp.batch = (int)B;
+        dp.tones = cv.take<double>(B * 2);
+        dp.lin_val = cv.take<double>(B * std::max(d.nlin, 1) * 2);
+        dp.src_val = cv.take<double>(B * std::max(d.nsrc, 1) * 3);
+        dp.diode_par = cv.take<double>(B * std::max(d.nd, 1) * YHB_DIODE_NPAR);
+        dp.bjt_par = cv.take<double>(B * std::max(d.nb, 1) * YHB_BJT_NPAR);
+        dp.cubic_par = cv.take<double>(B * std::max(d.nc, 1));
+        dr.V = cv.take<double>(B * W);
+        dr.Vf = cv.take<double>(B * d.N * K1 * 2);
+        dr.converged = cv.take<int32_t>(B);
+        dr.newton_iters = cv.take<int32_t>(B);
+        dr.lu_count = cv.take<int32_t>(B);
+        dr.level_iters = cv.take<int32_t>(B * YHB_MAX_LEVELS);
+        dr.level_alpha = cv.take<double>(B * YHB_MAX_LEVELS);
+        dr.err = cv.take<double>(B);
+        wsb = cv.take<char>(wsbytes);
+    };
+    const size_t wsbytes = yhb_workspace_bytes(pl, (int)B);
+    yhb_params dp;
+    yhb_result dr;
+    void *wsb;
+    plan_bytes(c, dp, dr, wsb, wsbytes);
+    const size_t need = align_up(c.off);
+    if (need > pl->hbuf_bytes) {
+        if (pl->hbuf) cudaFree(pl->hbuf);
+        pl->hbuf = nullptr;
+        pl->hbuf_bytes = 0;
+        YHB_CUDA(cudaMalloc(&pl->hbuf, need));
+        pl->hbuf_bytes = need;
+    }
+    Carver c2{reinterpret_cast<char *>(pl->hbuf), 0};
+    plan_bytes(c2, dp, dr, wsb, wsbytes);
+#define H2D(dst, src, cnt)                                                                                   \
+    do {                                                                                                     \
+        if ((cnt) > 0 && (src))                                                                              \
+            YHB_CUDA(cudaMemcpyAsync((void *)(dst), (src), (cnt) * sizeof(*(src)), cudaMemcpyHostToDevice, st)); \
+    } while (0)
+    H2D(dp.tones, hp->tones, B * 2);
+    H2D(dp.lin_val, hp->lin_val, B * d.nlin * 2);
+    H2D(dp.src_val, hp->src_val, B * d.nsrc * 3);
+    H2D(dp.diode_par, hp->diode_par, B * d.nd * YHB_DIODE_NPAR);
+    H2D(dp.bjt_par, hp->bjt_par, B * d.nb * YHB_BJT_NPAR);
+    H2D(dp.cubic_par, hp->cubic_par, B * d.nc);
+    if (V0) H2D(dr.V, V0, B * W);
+#undef H2D
+    if (int rc = yhb_dc_solve(pl, &dp, wsb, wsbytes, nullptr, nullptr, st)) return rc;
+    Layout L = carve(pl, (int)B, wsb);
+    if (int rc = yhb_solve(pl, &dp, opt, wsb, wsbytes, V0 != nullptr, L.ws.dcV, &dr, st)) return rc;
+#define D2H(dst, src, cnt)                                                                              \
+    do {                                                                                                \
+        if (dst) YHB_CUDA(cudaMemcpyAsync((dst), (src), (cnt) * sizeof(*(dst)), cudaMemcpyDeviceToHost, st)); \
+    } while (0)
+    D2H(hr->V, dr.V, B * W);
+    D2H(hr->Vf, dr.Vf, B * d.N * K1 * 2);
+    D2H(hr->converged, dr.converged, B);
+    D2H(hr->newton_iters, dr.newton_iters, B);
+    D2H(hr->lu_count, dr.lu_count, B);
+    D2H(hr->level_iters, dr.level_iters, B * YHB_MAX_LEVELS);
+    D2H(hr->level_alpha, dr.level_alpha, B * YHB_MAX_LEVELS);
+    D2H(hr->err, dr.err, B);
+#undef D2H
+    YHB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- stage entry points -----------------------------------------------------------------------------
+namespace yhb {
+
+__global__ void k_stage_ifft(PlanDev P, int batch, const double *V, double *vt) {
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    for (int i = threadIdx.x; i < P.W; i += blockDim.x) {
+        int n = i / P.S, s = i - n * P.S;
+        const double *row = P.idft + (size_t)s * P.S;
+        const double *x = V + (size_t)b * P.W + n * P.S;
+        double acc = 0.;
+        for (int c = 0; c < P.S; ++c) acc = fma(row[c], x[c], acc);
+        vt[(size_t)b * P.W + i] = acc;
+    }
+}
+
+// Stand-alone device sweep (:441-570): HBM in (vt, vtprev samples + raw model parameters), HBM out
+// (model outputs per sample).  One CTA per circuit; constants are derived once per device in shared memory.
+__global__ void __launch_bounds__(256) k_stage_device_eval(PlanDev P, int batch, const double *diode_par,
+                                                           const double *bjt_par, const double *cubic_par,
+                                                           const double *vt, const double *vtprev, double *diode_out,
+                                                           double *bjt_out, double *cubic_out) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    DiodeDerived *dd = reinterpret_cast<DiodeDerived *>(sm);
+    BjtDerived *bd = reinterpret_cast<BjtDerived *>(dd + P.nd);
+    for (int i = threadIdx.x; i < P.nd; i += blockDim.x)
+        diode_derive(diode_par + ((size_t)b * P.nd + i) * YHB_DIODE_NPAR, dd[i]);
+    for (int i = threadIdx.x; i < P.nb; i += blockDim.x)
+        bjt_derive(bjt_par + ((size_t)b * P.nb + i) * YHB_BJT_NPAR, P.flags, bd[i]);
+    __syncthreads();
+    const int S = P.S;
+    const double *v = vt + (size_t)b * P.W, *vo = vtprev + (size_t)b * P.W;
+    const int nitem = (P.nd + P.nc + P.nb) * S;
+    for (int it = threadIdx.x; it < nitem; it += blockDim.x) {
+        int dev = it / S, s = it - dev * S;
+        if (dev < P.nd + P.nc) {
+            const int *nodes = (dev < P.nd) ? P.diode_nodes + 2 * dev : P.cubic_nodes + 2 * (dev - P.nd);
+            int n1 = nodes[0] - 1, n2 = nodes[1] - 1;
+            double vd = (n1 >= 0 ? v[n1 * S + s] : 0.) - (n2 >= 0 ? v[n2 * S + s] : 0.);
+            double vdold = (n1 >= 0 ? vo[n1 * S + s] : 0.) - (n2 >= 0 ? vo[n2 * S + s] : 0.);
+            double g, I;
+            double *o;
+            if (dev < P.nd) {
+                diode_eval(dd[dev], vd, vdold, g, I);
+                o = diode_out + ((size_t)b * P.nd + dev) * 2 * S + s;
+            } else {
+                cubic_eval(cubic_par[(size_t)b * P.nc + dev - P.nd], vd, g, I);
+                o = cubic_out + ((size_t)b * P.nc + dev - P.nd) * 2 * S + s;
+            }
+            o[0] = g;
+            o[S] = I;
+        } else {
+            int q = dev - P.nd - P.nc;
+            const int *nodes = P.bjt_nodes + 3 * q;
+            int B = nodes[0] - 1, C = nodes[1] - 1, E = nodes[2] - 1;
+            double out[kBjtWaves];
+            bjt_eval(bd[q], B >= 0 ? v[B * S + s] : 0., C >= 0 ? v[C * S + s] : 0., E >= 0 ? v[E * S + s] : 0.,
+                     B >= 0 ? vo[B * S + s] : 0., C >= 0 ? vo[C * S + s] : 0., E >= 0 ? vo[E * S + s] : 0., out);
+            double *o = bjt_out + ((size_t)b * P.nb + q) * kBjtWaves * S + s;
+#pragma unroll
+            for (int j = 0; j < kBjtWaves; ++j) o[(size_t)j * S] = out[j];
+        }
+    }
+}
+
+}  // namespace yhb
+
+extern "C" int yhb_stage_ifft(const yhb_plan *pl, int32_t batch, const double *V, double *vt, void *stream) {
+    if (!pl || !V || !vt || batch < 1) { set_error("bad argument"); return -1; }
+    k_stage_ifft<<<batch, 256, 0, (cudaStream_t)stream>>>(pl->d, batch, V, vt);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int yhb_stage_device_eval(const yhb_plan *pl, const yhb_params *p, const double *vt, const double *vtprev,
+                                     double *diode_out, double *bjt_out, double *cubic_out, void *stream) {
+    if (int rc = check_params(pl, p)) return rc;
+    const PlanDev &d = pl->d;
+    if (!vt || !vtprev || (d.nd && !diode_out) || (d.nb && !bjt_out) || (d.nc && !cubic_out)) {
+        set_error("missing array");
+        return -1;
+    }
+    size_t smem = d.nd * sizeof(DiodeDerived) + d.nb * sizeof(BjtDerived);
+    if (smem > 48 * 1024)
+        YHB_CUDA(cudaFuncSetAttribute(k_stage_device_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stage_device_eval<<<p->batch, 256, smem, (cudaStream_t)stream>>>(d, p->batch, p->diode_par, p->bjt_par,
+                                                                       p->cubic_par, vt, vtprev, diode_out, bjt_out,
+                                                                       cubic_out);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int yhb_stage_assemble(const yhb_plan *pl, const yhb_params *p, void *wsbuf, size_t ws_bytes, const double *V,
+                                  const double *vtprev, const double *alpha, double *cacc, double *J, double *F,
+                                  void *stream) {
+    if (int rc = check_params(pl, p)) return rc;
+    if (!V || !J || !F) { set_error("missing array"); return -1; }
+    Layout L = carve(pl, p->batch, wsbuf);
+    if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
+    const PlanDev &d = pl->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)p->batch * d.W;
+    if (int rc = launch_prepare(pl, p, L, st)) return rc;
+    L.ws.V = const_cast<double *>(V);
+    L.ws.F = F;
+    L.ws.J = J;
+    L.ws.cacc = cacc;
+    L.ws.stage_first = vtprev == nullptr;
+    if (vtprev) YHB_CUDA(cudaMemcpyAsync(L.ws.vtprev, vtprev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    EvalArgs ea = eval_args(pl, p, nullptr, L);
+    ea.stage_only = 1;
+    ea.stage_alpha = alpha;
+    const int smem = eval_smem_bytes(pl, L);
+    if (int rc = ensure_eval_attr(smem)) return rc;
+    k_eval<<<p->batch, kEvalThreads, smem, st>>>(d, L.ws, ea);
+    dim3 ga(p->batch, (d.W + kAsmRows - 1) / kAsmRows);
+    k_assemble<<<ga, 256, 0, st>>>(d, L.ws, 0, 1);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int yhb_stage_lu(int32_t batch, int32_t W, double *J, const double *F, double *x, void *stream) {
+    if (batch < 1 || W < 1 || !J || !F || !x) { set_error("bad argument"); return -1; }
+    k_lu_stage<<<batch, kLuThreads, (W + 1) * sizeof(double), (cudaStream_t)stream>>>(batch, W, J, F, x);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}

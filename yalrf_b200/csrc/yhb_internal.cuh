@@ -1,0 +1,125 @@
+// Internal data structures of libyhb: the compiled plan (topology + stamp tables) and the
+// per-batch workspace carved out of the caller's scratch buffer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/yhb.h"
+
+namespace yhb {
+
+// waveform slots produced by the device sweep, per circuit: [nwave][S]
+//   diode d : base + 0 = gd, + 1 = Id
+//   cubic c : base + 0 = g,  + 1 = I
+//   bjt   q : base + 0..13 in BJT.get_hb_params return order (BJT.py:582)
+constexpr int kBjtWaves = 14;
+constexpr int kBjtCapBase = 10;  // Cbc, Cbe, Cbebc, Csc
+
+// A signed reference to a waveform slot (sign = +1 / -1), used by all stamp lists.
+struct Term {
+    int32_t idx;
+    int32_t sgn;
+};
+
+// Device-side view of the plan (all pointers are device pointers).
+struct PlanDev {
+    int N, K, S, W, ntones, K2;
+    int nlin, nsrc, nd, nb, nc, nwave;
+    int flags;
+    int npair;    // structurally nonzero node pairs (J blocks)
+    int npair_nl; // pairs with a nonlinear (dense) part; these come first in the pair list
+    const double *idft;  // [S][S]  x_s = sum_c idft[s][c] X_c   (:294-300)
+    const double *dft;   // [S][S]  X_r = sum_s dft[r][s] x_s    (:302)
+    const int *bin_k1;   // [K+1] tone multipliers of every bin: f = k1 f1 + k2 f2
+    const int *bin_k2;
+    const int *lin_kind;   // [nlin]
+    const int *src_kind;   // [nsrc]
+    const int *src_nodes;  // [nsrc][2]
+    const int *diode_nodes, *bjt_nodes, *cubic_nodes;  // reference numbering, 0 = gnd
+    const int *dev_wave_base;                          // [nd + nc + nb] first waveform slot of each device
+    // J block structure
+    const int *pair_n, *pair_m;  // [npair] 0-based nodes (row = KCL node, col = voltage node)
+    const int *pair_of;          // [N][N] -> pair index or -1
+    const int *row_ptr;          // [N+1] CSR over pairs sorted by (n, m)
+    const int *row_pairs;        // [npair]
+    // linear admittance terms per pair: element index, sign (Term.idx = linear element)
+    const int *plin_ptr;  // [npair+1]
+    const Term *plin;
+    // conductance / capacitance waveform terms per nonlinear pair (Term.idx = waveform slot)
+    const int *pg_ptr;  // [npair_nl+1]
+    const Term *pg;
+    const int *pc_ptr;  // [npair_nl+1]  (Term.idx = slot in the accumulated-capacitance array: q*4 + j)
+    const Term *pc;
+    // time-domain current / charge terms per node (Term.idx = waveform slot)
+    const int *ni_ptr;  // [N+1]
+    const Term *ni;
+    const int *nq_ptr;  // [N+1]
+    const Term *nq;
+    // independent-source terms per node (Term.idx = source index)
+    const int *ns_ptr;  // [N+1]
+    const Term *ns;
+};
+
+struct Plan {
+    PlanDev d;                  // device view
+    std::vector<void *> allocs; // device allocations owned by the plan
+    std::vector<int> bin_k1, bin_k2;
+    // host copies used by the DC solver setup
+    std::vector<int> lin_kind, lin_nodes, src_kind, src_nodes, diode_nodes, bjt_nodes, cubic_nodes;
+    const int *lin_nodes_dev;   // [nlin][4]
+    int num_inductors;
+    // cached buffers of yhb_run_host
+    void *host_ws;
+    size_t host_ws_bytes;
+};
+
+// Per-circuit Newton / continuation state (run() :330-387 and hb_loop :423-426 locals).
+struct Ctl {
+    int mode;       // 0 = direct attempt from V0, 1 = source-stepping ladder, 2 = done
+    int converged;  // final answer
+    int itercnt;    // Newton iterations of the current hb_loop
+    int first;      // next evaluation is the first of an hb_loop (no limiting, reset dQdV)
+    int level;      // continuation loop counter (:345)
+    int nlevels;    // hb_loop calls so far
+    int have_dv;    // a NaN-free Newton step exists (:624-627)
+    int newton, lus;
+    int fixed_alpha;  // yhb_newton: single hb_loop, no ladder
+    double alpha, inc, dec;
+    double err;
+};
+
+// Workspace layout for a batch (device pointers into the caller's scratch).
+struct Workspace {
+    int batch;
+    Ctl *ctl;            // [B]
+    double *V;           // [B][W]   current iterate (aliases res->V when given)
+    double *Vlevel;      // [B][W]   Vprev of the ladder (:339, :365)
+    double *dV;          // [B][W]   last NaN-free Newton step
+    double *vtprev;      // [B][W]   previous iterate's time samples (limiter reference)
+    double *F;           // [B][W]
+    double *cacc;        // [B][nb][4][S] accumulated capacitance waveforms (never-reset dQdV)
+    double *spec;        // [B][npair_nl][4][S]  reG, imG, reC, imC for m = 0..2K
+    double *ylin;        // [B][npair][K+1][2]
+    double *omega;       // [B][K+1]
+    int *negbin;         // [B][K+1] real frequency of the bin is negative (two-tone, :725)
+    int stage_first;     // stage entry points: treat the evaluation as the first of an hb_loop
+    double *Is;          // [B][W]  unscaled source vector (:647-684)
+    double *scratch;     // [B][scratch_stride] evaluation scratch when it does not fit shared memory
+    size_t scratch_stride;
+    double *J;           // [B][W][W]
+    int *list[2];        // [B] active-circuit lists (ping-pong)
+    int *count;          // [4] device counters: active[0], active[1], done, spare
+    int32_t *level_iters;  // [B][YHB_MAX_LEVELS]
+    double *level_alpha;   // [B][YHB_MAX_LEVELS]
+    double *dcV;         // [B][N] DC node voltages
+    int *dcinfo;         // [B][2]
+    double *dcscratch;   // DC solver scratch
+    size_t dc_stride;
+};
+
+void set_error(const std::string &msg);
+
+}  // namespace yhb
