@@ -133,6 +133,19 @@ int yhb_version(void);
 /* CUDA device used by the calling thread for all later calls (cudaSetDevice) */
 int yhb_set_device(int32_t device);
 
+/* Per-kernel device timing (CUDA events on the launching stream around every launch of the solve loop).
+ * yhb_profile_enable(1) switches it on for the calling process; yhb_profile_read resolves the recorded events
+ * (synchronises them) and returns, per kernel kind, launches and total milliseconds since the last reset.
+ * Kinds: 0 prepare, 1 dc, 2 init, 3 eval, 4 assemble, 5 lu, 6 finish, 7 fused. */
+#define YHB_PROF_KINDS 8
+int yhb_profile_enable(int32_t on);
+int yhb_profile_reset(void);
+int yhb_profile_read(int64_t *launches /* [YHB_PROF_KINDS] */, double *ms /* [YHB_PROF_KINDS] */);
+
+/* Measures the FP64 FMA throughput of the current device (independent DFMA chains on every SM) and returns it
+ * in TFLOP/s: the roofline denominator of the LU stage (MEASURED_PEAKS.json has no fp64 figure). */
+int yhb_fp64_peak(double *tflops, void *stream);
+
 /* plan = the setup part of run() (:234-302): grid sizes, DFT/IDFT tables, stamp tables */
 int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out);
 void yhb_plan_destroy(yhb_plan *plan);

@@ -141,7 +141,15 @@ def test_peltz_probe_fixed(yb, golden):
     conv, freqs, Vf, _, _ = hb.run(y)
     assert conv
     assert hb.last.levels() == g['iters'].tolist()
-    assert relmax(hb.V, g['V']) < 1e-9
+    V, G = hb.V.reshape(hb.N, hb.S), g['V'].reshape(hb.N, hb.S)
+    probe = y.get_node_idx('P.n1') - 1
+    for n in range(hb.N):
+        if n != probe:
+            assert np.max(np.abs(V[n] - G[n])) < 1e-9 * np.max(np.abs(G)), n
+    # V('P.n1') is the probe CURRENT (gyrator), i.e. 1e9 S * (V(P.n2) - V(nb)): one ulp of the 0.7 V phasors is
+    # 1.1e-16 V = 1.1e-7 A.  The reference's own value carries that rounding noise, so it is
+    # pinned to a few ulps of the filter voltage, not to 1e-9 relative.  Measured on B200: 1.9e-7.
+    assert np.max(np.abs(V[probe] - G[probe])) < 1e9 * 8 * np.spacing(0.7)
 
 
 def test_ladder(yb, golden):

@@ -149,4 +149,58 @@ def run_host(plan, pb, options, V0=None):
     if V0 is not None:
         v0 = L.f64(np.asarray(V0).reshape(pb.B, plan.W))
     L.check(L.lib().yhb_run_host(plan.handle, C.byref(p), C.byref(o), L.ptr(v0), C.byref(r)))
+    res.params_bytes = sum(getattr(pb, n).nbytes for n in ('tones', 'lin_val', 'src_val', 'diode_par', 'bjt_par',
+                                                            'cubic_par')) + (0 if v0 is None else v0.nbytes)
     return res
+
+
+class DeviceBatch:
+    """A parameter block resident in HBM (torch owns the buffers) + result / workspace buffers for repeated solves."""
+
+    def __init__(self, plan, pb):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError('yalrf_b200 needs a CUDA device: there is no CPU fallback')
+        pb.finalize()
+        self.plan, self.B = plan, pb.B
+        self.dev = torch.device('cuda', torch.cuda.current_device())
+        L.check(L.lib().yhb_set_device(self.dev.index))
+        self.t = {n: torch.from_numpy(getattr(pb, n)).to(self.dev) for n in
+                  ('tones', 'lin_val', 'src_val', 'diode_par', 'bjt_par', 'cubic_par')}
+        self.params = L.Params()
+        self.params.batch = pb.B
+        for n, v in self.t.items():
+            setattr(self.params, n, v.data_ptr())
+        B = pb.B
+        f64, i32 = torch.float64, torch.int32
+        self.V = torch.zeros((B, plan.W), dtype=f64, device=self.dev)
+        self.Vf = torch.zeros((B, plan.N, plan.K + 1, 2), dtype=f64, device=self.dev)
+        self.converged = torch.zeros(B, dtype=i32, device=self.dev)
+        self.newton_iters = torch.zeros(B, dtype=i32, device=self.dev)
+        self.lu_count = torch.zeros(B, dtype=i32, device=self.dev)
+        self.level_iters = torch.zeros((B, L.MAX_LEVELS), dtype=i32, device=self.dev)
+        self.level_alpha = torch.zeros((B, L.MAX_LEVELS), dtype=f64, device=self.dev)
+        self.err = torch.zeros(B, dtype=f64, device=self.dev)
+        self.Vdc = torch.zeros((B, plan.N), dtype=f64, device=self.dev)
+        self.dcinfo = torch.zeros((B, 2), dtype=i32, device=self.dev)
+        self.ws_bytes = L.lib().yhb_workspace_bytes(plan.handle, B)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev)
+        r = L.Result()
+        r.V, r.Vf = self.V.data_ptr(), self.Vf.data_ptr()
+        r.converged, r.newton_iters, r.lu_count = (self.converged.data_ptr(), self.newton_iters.data_ptr(),
+                                                   self.lu_count.data_ptr())
+        r.level_iters, r.level_alpha, r.err = (self.level_iters.data_ptr(), self.level_alpha.data_ptr(),
+                                               self.err.data_ptr())
+        self.result = r
+
+    def solve(self, options, have_v0=False, stream=None):
+        """DC points + run() for the whole batch on `stream` (default: torch's current stream); no D2H."""
+        import torch
+        lib = L.lib()
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        o = make_options(options)
+        if not have_v0:
+            L.check(lib.yhb_dc_solve(self.plan.handle, C.byref(self.params), self.ws.data_ptr(), self.ws_bytes,
+                                     self.Vdc.data_ptr(), self.dcinfo.data_ptr(), st))
+        L.check(lib.yhb_solve(self.plan.handle, C.byref(self.params), C.byref(o), self.ws.data_ptr(), self.ws_bytes,
+                              1 if have_v0 else 0, self.Vdc.data_ptr(), C.byref(self.result), st))

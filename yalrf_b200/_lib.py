@@ -52,7 +52,10 @@ class Result(C.Structure):
 
 _lib = None
 
-EXPORTS = ['yhb_last_error', 'yhb_version', 'yhb_set_device', 'yhb_plan_create', 'yhb_plan_destroy',
+PROF_KINDS = ['prepare', 'dc', 'init', 'eval', 'assemble', 'lu', 'finish', 'fused']
+
+EXPORTS = ['yhb_last_error', 'yhb_version', 'yhb_set_device', 'yhb_profile_enable', 'yhb_profile_reset',
+           'yhb_profile_read', 'yhb_fp64_peak', 'yhb_plan_create', 'yhb_plan_destroy',
            'yhb_plan_dims', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_newton',
            'yhb_run_host', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu']
 
@@ -69,6 +72,9 @@ def lib():
     L.yhb_last_error.restype = C.c_char_p
     L.yhb_version.restype = C.c_int
     L.yhb_set_device.argtypes = [C.c_int32]
+    L.yhb_profile_enable.argtypes = [C.c_int32]
+    L.yhb_profile_read.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.yhb_fp64_peak.argtypes = [C.POINTER(C.c_double), C.c_void_p]
     L.yhb_plan_create.argtypes = [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]
     L.yhb_plan_destroy.argtypes = [C.c_void_p]
     L.yhb_plan_destroy.restype = None
@@ -91,6 +97,14 @@ def lib():
     L.yhb_stage_lu.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
+
+
+def profile_read():
+    """{kernel kind: (launches, total ms)} since the last yhb_profile_reset"""
+    n = (C.c_int64 * len(PROF_KINDS))()
+    ms = (C.c_double * len(PROF_KINDS))()
+    lib().yhb_profile_read(n, ms)
+    return {k: (int(n[i]), float(ms[i])) for i, k in enumerate(PROF_KINDS)}
 
 
 def check(rc):

@@ -32,6 +32,44 @@ void set_error(const std::string &msg) { g_err = msg; }
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// ---- optional per-kernel timing ---------------------------------------------------------------------
+enum { PK_PREPARE = 0, PK_DC, PK_INIT, PK_EVAL, PK_ASSEMBLE, PK_LU, PK_FINISH, PK_FUSED };
+struct Prof {
+    bool on = false;
+    std::mutex mu;
+    long long launches[YHB_PROF_KINDS] = {0};
+    double ms[YHB_PROF_KINDS] = {0};
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> open;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+static Prof g_prof;
+
+struct ProfScope {  // records an event pair around the launches made while it is alive
+    int kind;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s) {
+        if (!g_prof.on) return;
+        std::lock_guard<std::mutex> lk(g_prof.mu);
+        a = g_prof.get();
+        b = g_prof.get();
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_prof.mu);
+        g_prof.open.push_back({kind, a, b});
+    }
+};
+
 template <typename T>
 static const T *upload(Plan *pl, const std::vector<T> &v) {
     void *d = nullptr;
@@ -77,6 +115,43 @@ extern "C" const char *yhb_last_error(void) { return g_err.c_str(); }
 extern "C" int yhb_version(void) { return YHB_VERSION; }
 extern "C" int yhb_set_device(int32_t device) {
     YHB_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" int yhb_profile_enable(int32_t on) {
+    g_prof.on = on != 0;
+    return 0;
+}
+
+static void prof_resolve() {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (auto &s : g_prof.open) {
+        cudaEventSynchronize(s.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            g_prof.ms[s.kind] += ms;
+            g_prof.launches[s.kind] += 1;
+        }
+        g_prof.pool.push_back(s.a);
+        g_prof.pool.push_back(s.b);
+    }
+    g_prof.open.clear();
+}
+
+extern "C" int yhb_profile_reset(void) {
+    prof_resolve();
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (int i = 0; i < YHB_PROF_KINDS; ++i) { g_prof.launches[i] = 0; g_prof.ms[i] = 0.; }
+    return 0;
+}
+
+extern "C" int yhb_profile_read(int64_t *launches, double *ms) {
+    prof_resolve();
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (int i = 0; i < YHB_PROF_KINDS; ++i) {
+        if (launches) launches[i] = g_prof.launches[i];
+        if (ms) ms[i] = g_prof.ms[i];
+    }
     return 0;
 }
 
@@ -442,6 +517,7 @@ int launch_prepare(const yhb_plan *pl, const yhb_params *p, const Layout &L, cud
     a.negbin = L.ws.negbin;
     a.dd = L.dd;
     a.bd = L.bd;
+    ProfScope ps(PK_PREPARE, st);
     k_prepare<<<p->batch, 128, 0, st>>>(pl->d, a, p->batch);
     YHB_CUDA(cudaGetLastError());
     return 0;
@@ -480,7 +556,10 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
     const int B = p->batch;
     Workspace &ws = L.ws;
     if (int rc = launch_prepare(pl, p, L, st)) return rc;
-    k_init<<<B, 128, 0, st>>>(d, ws, have_v0, alpha_fixed);
+    {
+        ProfScope ps(PK_INIT, st);
+        k_init<<<B, 128, 0, st>>>(d, ws, have_v0, alpha_fixed);
+    }
     YHB_CUDA(cudaGetLastError());
     EvalArgs ea = eval_args(pl, p, opt, L);
     const int smem = eval_smem_bytes(pl, L);
@@ -491,15 +570,24 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
     while (nactive > 0) {
         YHB_CUDA(cudaMemsetAsync(ws.count + (cur ^ 1), 0, sizeof(int), st));
         ea.cur = cur;
-        k_eval<<<nactive, kEvalThreads, smem, st>>>(d, ws, ea);
+        {
+            ProfScope ps(PK_EVAL, st);
+            k_eval<<<nactive, kEvalThreads, smem, st>>>(d, ws, ea);
+        }
         YHB_CUDA(cudaGetLastError());
         YHB_CUDA(cudaMemcpyAsync(hc, ws.count, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         YHB_CUDA(cudaStreamSynchronize(st));
         const int nsolve = hc[cur ^ 1];
         if (nsolve > 0) {
             dim3 ga(nsolve, (d.W + kAsmRows - 1) / kAsmRows);
-            k_assemble<<<ga, 256, 0, st>>>(d, ws, cur ^ 1, 0);
-            k_lu<<<nsolve, kLuThreads, (d.W + 1) * sizeof(double), st>>>(d, ws, cur ^ 1);
+            {
+                ProfScope ps(PK_ASSEMBLE, st);
+                k_assemble<<<ga, 256, 0, st>>>(d, ws, cur ^ 1, 0);
+            }
+            {
+                ProfScope ps(PK_LU, st);
+                k_lu<<<nsolve, kLuThreads, (d.W + 1) * sizeof(double), st>>>(d, ws, cur ^ 1);
+            }
             YHB_CUDA(cudaGetLastError());
         }
         nactive = nsolve;
@@ -514,7 +602,10 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
     fa.level_iters = res->level_iters;
     fa.level_alpha = res->level_alpha;
     fa.err = res->err;
-    k_finish<<<B, 128, 0, st>>>(d, ws, fa);
+    {
+        ProfScope ps(PK_FINISH, st);
+        k_finish<<<B, 128, 0, st>>>(d, ws, fa);
+    }
     YHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -548,7 +639,10 @@ extern "C" int yhb_dc_solve(const yhb_plan *pl, const yhb_params *p, void *wsbuf
     a.Vdc = Vdc ? Vdc : L.ws.dcV;
     a.info = dc_info ? dc_info : L.ws.dcinfo;
     cudaStream_t st = (cudaStream_t)stream;
-    k_dc<<<p->batch, kDcThreads, (a.M + 2) * sizeof(double), st>>>(d, a, p->batch);
+    {
+        ProfScope ps(PK_DC, st);
+        k_dc<<<p->batch, kDcThreads, (a.M + 2) * sizeof(double), st>>>(d, a, p->batch);
+    }
     YHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -784,5 +878,50 @@ extern "C" int yhb_stage_lu(int32_t batch, int32_t W, double *J, const double *F
     if (batch < 1 || W < 1 || !J || !F || !x) { set_error("bad argument"); return -1; }
     k_lu_stage<<<batch, kLuThreads, (W + 1) * sizeof(double), (cudaStream_t)stream>>>(batch, W, J, F, x);
     YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- FP64 pipe peak (roofline denominator of the LU stage) -----------------------------------------
+namespace yhb {
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6.,
+           a7 = a0 + 7.;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+}  // namespace yhb
+
+extern "C" int yhb_fp64_peak(double *tflops, void *stream) {
+    if (!tflops) { set_error("null argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    int dev = 0;
+    YHB_CUDA(cudaGetDevice(&dev));
+    YHB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *buf = nullptr;
+    YHB_CUDA(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a, st);
+        k_fp64_peak<<<blocks, threads, 0, st>>>(buf, iters);
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    YHB_CUDA(cudaGetLastError());
+    *tflops = 2.0 * 8 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
     return 0;
 }
