@@ -191,3 +191,67 @@ def test_nonconvergence_is_data(yb):
     hb.options['maxiter'] = 20
     out = hb.run(y)
     assert out == (False, None, None, None, None)
+
+
+# ----------------------------------------------------------------------------- engines: fused / staged / unpeeled
+@pytest.mark.parametrize('engine,peel', [('auto', True), ('staged', True), ('staged', False), ('auto', False)])
+def test_engines_agree_with_golden(yb, golden, engine, peel):
+    """The fused on-chip engine, the staged engine, and the unpeeled (full W x W) factorisation all reproduce the
+    reference: DiffAmp cold grid (subset), HB_Diode, two tones [3,3], Peltz with probe."""
+    g = golden('diffamp_cold_grid')
+    y = yb.YalRF('Differential Amplifier')
+    h = circuits.diffamp(y)
+    vb, vin = np.meshgrid(g['vbs'], g['vins'], indexing='ij')
+    vb, vin = vb.ravel(), vin.ravel()
+    hb = mthb('HB1', h['freq'], h['K'])
+    hb.engine, hb.peel = engine, peel
+    res = hb.run_sweep(y, [(h['i2'], 'ac', vin / 2), (h['i4'], 'ac', vin / 2), (h['i3'], 'dc', vb), (h['i5'], 'dc', vb)])
+    Nc, Wc, fused = hb._plan.core()
+    assert fused == (engine == 'auto')
+    assert Wc == (84 if peel else 210)
+    for k in range(len(vb)):
+        its = g['iters'][k]
+        assert res.levels(k) == its[its > 0].tolist(), (k, engine, peel)
+        assert relmax(res.V[k], g['V'][k][:, 0]) < 1e-9, (k, engine, peel)
+
+    g = golden('hb_diode')
+    y = yb.YalRF('d')
+    h = circuits.hb_diode(y)
+    hb = mthb('HB1', h['freq'], h['K'])
+    hb.engine, hb.peel = engine, peel
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert hb._plan.core()[1] == (21 if peel else 63)
+    assert conv and hb.last.levels() == g['iters'].tolist()
+    assert relmax(hb.V, g['V']) < 1e-9
+
+    g = golden('two_tones_3x3')
+    y = yb.YalRF('d')
+    h = circuits.hb_diode_two_tones(y)
+    hb = mthb('HB1', h['freq'], [3, 3])
+    hb.engine, hb.peel = engine, peel
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert hb._plan.core()[1] == (49 if peel else 245)
+    assert conv and hb.last.levels() == g['iters'].tolist()
+    assert relmax(hb.V, g['V']) < 1e-9
+
+
+def test_warm_start_failure_falls_back_to_ladder(yb):
+    """run(y, V0) with a useless V0: the direct attempt fails, the engine restarts from the DC point (:333-345) and
+    lands on the cold-start answer; the oracle does the same."""
+    from oracle import hb_oracle as ho
+    y = yb.YalRF('d')
+    h = circuits.hb_diode(y)
+    hb = mthb('HB1', h['freq'], h['K'])
+    hb.options['maxiter'] = 8
+    rng = np.random.default_rng(3)
+    V0 = rng.normal(scale=3.0, size=(63, 1))
+    conv, freqs, Vf, _, _ = hb.run(y, V0)
+    yo = ho.FlatNetlist()
+    circuits.hb_diode(yo)
+    o = ho.HBOracle('HB1', h['freq'], h['K'])
+    o.options['maxiter'] = 8
+    conv_o = o.run(yo, V0.copy())[0]
+    assert conv == conv_o
+    assert hb.last.levels() == [l[1] for l in o.level_log]
+    if conv:
+        assert relmax(hb.V, o.V) < 1e-9

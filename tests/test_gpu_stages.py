@@ -147,7 +147,10 @@ def test_assemble_and_lu_vs_oracle(name, nh, kw):
         if t['dV'] is not None:
             L.check(lib.yhb_stage_lu(1, W, J.data_ptr(), F.data_ptr(), x.data_ptr(), None))
             torch.cuda.synchronize()
-            assert relmax(x.cpu().numpy()[0], t['dV'][:, 0]) < 1e-8, ('dV', it)
+            xh = x.cpu().numpy()[0]
+            assert relmax(xh, np.linalg.solve(Jh, Fh)) < 1e-9, ('solve', it)
+            if np.max(np.abs(t['F'])) > 1e-6:   # below that F is rounding noise, and so is the reference's dV
+                assert relmax(xh, t['dV'][:, 0]) < 1e-8, ('dV', it)
 
 
 def test_stage_ifft_vs_numpy():

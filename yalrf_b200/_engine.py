@@ -58,6 +58,12 @@ class Plan:
         L.check(lib.yhb_plan_create(C.byref(d), C.byref(h)))
         self.handle = h
 
+    def core(self):
+        """(Nc, Wc, fused): dense core left after peeling the ideal-source rows, and the engine that will run"""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        L.check(L.lib().yhb_plan_core(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, bool(c.value)
+
     def freqs(self, f1, f2=0.0):
         out = np.zeros(self.K + 1)
         L.check(L.lib().yhb_plan_freqs(self.handle, float(f1), float(f2), out.ctypes.data_as(C.POINTER(C.c_double))))
@@ -149,6 +155,7 @@ def run_host(plan, pb, options, V0=None):
     if V0 is not None:
         v0 = L.f64(np.asarray(V0).reshape(pb.B, plan.W))
     L.check(L.lib().yhb_run_host(plan.handle, C.byref(p), C.byref(o), L.ptr(v0), C.byref(r)))
+    res.core_W = plan.core()[1]
     res.params_bytes = sum(getattr(pb, n).nbytes for n in ('tones', 'lin_val', 'src_val', 'diode_par', 'bjt_par',
                                                             'cubic_par')) + (0 if v0 is None else v0.nbytes)
     return res

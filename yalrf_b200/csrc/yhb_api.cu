@@ -323,6 +323,82 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
         if (n2 > 0) ns.add(n2 - 1, s, -1);
     }
 
+    // ---- structural peeling of ideal-source rows / columns (gyrator pivots are exactly +-1: no rounding, no
+    // growth).  Reference netlists model every voltage source as current source + gyrator
+    // (tests/HB_Diode.py:12-13), which leaves rows with a single unknown and unknowns that appear in a single
+    // row; eliminating them symbolically shrinks the dense system LAPACK would factor (:620) from W to Wc.
+    std::vector<int> unit_sign(d.npair, 0);
+    for (int p = 0; p < d.npair; ++p) {
+        if (p < d.npair_nl) continue;
+        const auto &row = p < (int)plin.rows.size() ? plin.rows[p] : std::vector<Term>();
+        if (row.size() == 1 && pl->lin_kind[row[0].idx] == YHB_LIN_GYRATOR) unit_sign[p] = row[0].sgn;
+    }
+    std::vector<std::vector<int>> row_cols(N), col_rows(N);  // pairs by row / by column
+    for (int p = 0; p < d.npair; ++p) {
+        row_cols[pairs[p].first].push_back(p);
+        col_rows[pairs[p].second].push_back(p);
+    }
+    std::vector<char> act_row(N, 1), act_col(N, 1), a_known(N, 0);
+    std::vector<int> a_row, a_col, a_sgn, b_row, b_col, b_sgn;
+    if (!(desc->flags & YHB_FLAG_NO_PEEL)) {
+        bool changed = true;
+        while (changed) {
+            changed = false;
+            for (int n = 0; n < N; ++n) {  // row singletons
+                if (!act_row[n]) continue;
+                int cnt = 0, last = -1;
+                for (int p : row_cols[n])
+                    if (!a_known[pairs[p].second]) { ++cnt; last = p; }
+                if (cnt == 1 && unit_sign[last] != 0 && act_col[pairs[last].second]) {
+                    a_row.push_back(n);
+                    a_col.push_back(pairs[last].second);
+                    a_sgn.push_back(unit_sign[last]);
+                    act_row[n] = 0;
+                    act_col[pairs[last].second] = 0;
+                    a_known[pairs[last].second] = 1;
+                    changed = true;
+                }
+            }
+            for (int m = 0; m < N; ++m) {  // column singletons
+                if (!act_col[m]) continue;
+                int cnt = 0, last = -1;
+                for (int p : col_rows[m])
+                    if (act_row[pairs[p].first]) { ++cnt; last = p; }
+                if (cnt == 1 && unit_sign[last] != 0) {
+                    b_row.push_back(pairs[last].first);
+                    b_col.push_back(m);
+                    b_sgn.push_back(unit_sign[last]);
+                    act_row[pairs[last].first] = 0;
+                    act_col[m] = 0;
+                    changed = true;
+                }
+            }
+        }
+    }
+    std::vector<int> core_rows, core_cols, core_col_of(N, -1);
+    for (int n = 0; n < N; ++n) if (act_row[n]) core_rows.push_back(n);
+    for (int n = 0; n < N; ++n) if (act_col[n]) { core_col_of[n] = (int)core_cols.size(); core_cols.push_back(n); }
+    d.Nc = (int)core_rows.size();
+    d.Wc = d.Nc * S;
+    d.nA = (int)a_row.size();
+    d.nB = (int)b_row.size();
+    std::vector<int> a_ptr(1, 0), a_pair, a_m, b_ptr(1, 0), b_pair, b_m, r_ptr(1, 0), r_pair, r_m;
+    for (int a = 0; a < d.nA; ++a) {  // the other entries of an A row (all A-known by construction)
+        for (int p : row_cols[a_row[a]])
+            if (pairs[p].second != a_col[a]) { a_pair.push_back(p); a_m.push_back(pairs[p].second); }
+        a_ptr.push_back((int)a_pair.size());
+    }
+    for (int b = 0; b < d.nB; ++b) {
+        for (int p : row_cols[b_row[b]])
+            if (pairs[p].second != b_col[b]) { b_pair.push_back(p); b_m.push_back(pairs[p].second); }
+        b_ptr.push_back((int)b_pair.size());
+    }
+    for (int r = 0; r < d.Nc; ++r) {  // entries of a core row in A-known columns move to the right-hand side
+        for (int p : row_cols[core_rows[r]])
+            if (a_known[pairs[p].second]) { r_pair.push_back(p); r_m.push_back(pairs[p].second); }
+        r_ptr.push_back((int)r_pair.size());
+    }
+
     std::vector<int> pair_n, pair_m, pair_of((size_t)N * N, -1);
     for (int p = 0; p < d.npair; ++p) {
         pair_n.push_back(pairs[p].first);
@@ -382,6 +458,10 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     ni.flatten(N, ptr, terms); UP(ni_ptr, ptr); UP(ni, terms);
     nq.flatten(N, ptr, terms); UP(nq_ptr, ptr); UP(nq, terms);
     ns.flatten(N, ptr, terms); UP(ns_ptr, ptr); UP(ns, terms);
+    UP(core_rows, core_rows); UP(core_cols, core_cols); UP(core_col_of, core_col_of);
+    UP(a_row, a_row); UP(a_col, a_col); UP(a_sgn, a_sgn); UP(a_ptr, a_ptr); UP(a_pair, a_pair); UP(a_m, a_m);
+    UP(b_row, b_row); UP(b_col, b_col); UP(b_sgn, b_sgn); UP(b_ptr, b_ptr); UP(b_pair, b_pair); UP(b_m, b_m);
+    UP(r_ptr, r_ptr); UP(r_pair, r_pair); UP(r_m, r_m);
 #undef UP
     pl->lin_nodes_dev = upload(pl, pl->lin_nodes);
     pl->nl_kind_dev = upload(pl, pl->nl_kind);
@@ -419,6 +499,14 @@ extern "C" int yhb_plan_dims(const yhb_plan *pl, int32_t *N, int32_t *K, int32_t
     return 0;
 }
 
+extern "C" int yhb_plan_core(const yhb_plan *pl, int32_t *Nc, int32_t *Wc, int32_t *fused) {
+    if (!pl) { set_error("null plan"); return -1; }
+    if (Nc) *Nc = pl->d.Nc;
+    if (Wc) *Wc = pl->d.Wc;
+    if (fused) *fused = fused_smem_doubles(pl->d) * sizeof(double) <= 227 * 1024 && !(pl->d.flags & YHB_FLAG_STAGED);
+    return 0;
+}
+
 extern "C" int yhb_plan_freqs(const yhb_plan *pl, double f1, double f2, double *freqs) {
     if (!pl || !freqs) { set_error("null argument"); return -1; }
     for (int k = 0; k <= pl->d.K; ++k)
@@ -442,6 +530,7 @@ struct Carver {
 };
 
 constexpr size_t kMaxEvalSmem = 200 * 1024;
+constexpr size_t kMaxFusedSmem = 227 * 1024;
 
 struct Layout {
     Workspace ws;
@@ -449,6 +538,7 @@ struct Layout {
     BjtDerived *bd;
     size_t bytes;
     bool eval_smem;
+    bool fused;
 };
 
 Layout carve(const yhb_plan *pl, int B, void *base) {
@@ -475,7 +565,11 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     L.eval_smem = esd * sizeof(double) <= kMaxEvalSmem;
     ws.scratch_stride = L.eval_smem ? 0 : esd;
     ws.scratch = c.take<double>(L.eval_smem ? 1 : (size_t)B * esd);
-    ws.J = c.take<double>((size_t)B * W * W);
+    L.fused = fused_smem_doubles(d) * sizeof(double) <= kMaxFusedSmem && !(d.flags & YHB_FLAG_STAGED);
+    ws.j_stride = L.fused ? 0 : (size_t)d.Wc * d.Wc;
+    ws.J = c.take<double>(L.fused ? 1 : (size_t)B * ws.j_stride);
+    ws.xstep = c.take<double>(L.fused ? 1 : B * W);
+    ws.rhs = c.take<double>(L.fused ? 1 : (size_t)B * (d.Wc + 1));
     ws.list[0] = c.take<int>(B);
     ws.list[1] = c.take<int>(B);
     ws.count = c.take<int>(4);
@@ -549,6 +643,23 @@ int ensure_eval_attr(int bytes) {
     return 0;
 }
 
+int launch_finish(const yhb_plan *pl, Layout &L, const yhb_result *res, cudaStream_t st) {
+    FinishArgs fa;
+    fa.Vf = res->Vf;
+    fa.converged = res->converged;
+    fa.newton_iters = res->newton_iters;
+    fa.lu_count = res->lu_count;
+    fa.level_iters = res->level_iters;
+    fa.level_alpha = res->level_alpha;
+    fa.err = res->err;
+    {
+        ProfScope ps(PK_FINISH, st);
+        k_finish<<<L.ws.batch, 128, 0, st>>>(pl->d, L.ws, fa);
+    }
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // the Newton / continuation launch loop shared by yhb_solve and yhb_newton
 int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, Layout &L, int have_v0,
              const double *alpha_fixed, const yhb_result *res, cudaStream_t st) {
@@ -562,6 +673,26 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
     }
     YHB_CUDA(cudaGetLastError());
     EvalArgs ea = eval_args(pl, p, opt, L);
+    if (L.fused) {
+        const int fsmem = (int)(fused_smem_doubles(d) * sizeof(double));
+        static int fused_cfg = 0;
+        if (fsmem > fused_cfg) {
+            YHB_CUDA(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxFusedSmem));
+            fused_cfg = (int)kMaxFusedSmem;
+        }
+        int per_sm = 0;
+        YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused, kFusedThreads, fsmem));
+        int dev = 0, sms = 0;
+        YHB_CUDA(cudaGetDevice(&dev));
+        YHB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int grid = std::min(B, std::max(1, per_sm) * sms);  // persistent CTAs pulling circuits from a queue
+        {
+            ProfScope ps(PK_FUSED, st);
+            k_fused<<<grid, kFusedThreads, fsmem, st>>>(d, ws, ea);
+        }
+        YHB_CUDA(cudaGetLastError());
+        return launch_finish(pl, L, res, st);
+    }
     const int smem = eval_smem_bytes(pl, L);
     if (int rc = ensure_eval_attr(smem)) return rc;
     int cur = 0, nactive = B;
@@ -579,14 +710,14 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
         YHB_CUDA(cudaStreamSynchronize(st));
         const int nsolve = hc[cur ^ 1];
         if (nsolve > 0) {
-            dim3 ga(nsolve, (d.W + kAsmRows - 1) / kAsmRows);
-            {
+            if (d.Wc > 0) {
+                dim3 ga(nsolve, (d.Wc + kAsmRows - 1) / kAsmRows);
                 ProfScope ps(PK_ASSEMBLE, st);
-                k_assemble<<<ga, 256, 0, st>>>(d, ws, cur ^ 1, 0);
+                k_assemble_core<<<ga, 256, 0, st>>>(d, ws, ea, cur ^ 1);
             }
             {
                 ProfScope ps(PK_LU, st);
-                k_lu<<<nsolve, kLuThreads, (d.W + 1) * sizeof(double), st>>>(d, ws, cur ^ 1);
+                k_solve_core<<<nsolve, kLuThreads, (d.Wc + 2) * sizeof(double), st>>>(d, ws, ea, cur ^ 1);
             }
             YHB_CUDA(cudaGetLastError());
         }
@@ -594,20 +725,7 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
         cur ^= 1;
         if (++rounds > 100000) { set_error("Newton launch loop did not terminate"); return -4; }
     }
-    FinishArgs fa;
-    fa.Vf = res->Vf;
-    fa.converged = res->converged;
-    fa.newton_iters = res->newton_iters;
-    fa.lu_count = res->lu_count;
-    fa.level_iters = res->level_iters;
-    fa.level_alpha = res->level_alpha;
-    fa.err = res->err;
-    {
-        ProfScope ps(PK_FINISH, st);
-        k_finish<<<B, 128, 0, st>>>(d, ws, fa);
-    }
-    YHB_CUDA(cudaGetLastError());
-    return 0;
+    return launch_finish(pl, L, res, st);
 }
 
 }  // namespace
@@ -869,7 +987,7 @@ extern "C" int yhb_stage_assemble(const yhb_plan *pl, const yhb_params *p, void 
     if (int rc = ensure_eval_attr(smem)) return rc;
     k_eval<<<p->batch, kEvalThreads, smem, st>>>(d, L.ws, ea);
     dim3 ga(p->batch, (d.W + kAsmRows - 1) / kAsmRows);
-    k_assemble<<<ga, 256, 0, st>>>(d, L.ws, 0, 1);
+    k_assemble<<<ga, 256, 0, st>>>(d, L.ws, ea);
     YHB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -61,6 +61,18 @@ struct PlanDev {
     // independent-source terms per node (Term.idx = source index)
     const int *ns_ptr;  // [N+1]
     const Term *ns;
+    // ---- dense core after structural peeling of ideal-source rows / columns (see peel() in yhb_api.cu)
+    // A-steps (row singletons, unit gyrator pivot): dV[col] = sgn * (F[row] - sum_others J[row,m] dV[m]), in order.
+    // B-steps (column singletons): the same formula, evaluated in REVERSE order after the core solve.
+    // Core: J[core_rows, core_cols] y = F[core_rows] - sum_{A-known m} J[row, m] dV[m].
+    int Nc, Wc, nA, nB;
+    const int *core_rows, *core_cols;  // [Nc] node indices
+    const int *core_col_of;            // [N] -> position among core_cols or -1
+    const int *a_row, *a_col, *a_sgn;  // [nA]
+    const int *a_ptr, *a_pair, *a_m;   // other entries of each A row: CSR [nA+1], pair index, column node
+    const int *b_row, *b_col, *b_sgn;  // [nB]
+    const int *b_ptr, *b_pair, *b_m;
+    const int *r_ptr, *r_pair, *r_m;   // per core row: entries in A-known columns, CSR [Nc+1]
 };
 
 struct Plan {
@@ -109,7 +121,10 @@ struct Workspace {
     double *Is;          // [B][W]  unscaled source vector (:647-684)
     double *scratch;     // [B][scratch_stride] evaluation scratch when it does not fit shared memory
     size_t scratch_stride;
-    double *J;           // [B][W][W]
+    double *J;           // staged engine: core Jacobians [B][j_stride] (stage entry point: caller's full [B][W][W])
+    size_t j_stride;
+    double *xstep;       // [B][W]  staged engine: Newton step work vector
+    double *rhs;         // [B][Wc+1]
     int *list[2];        // [B] active-circuit lists (ping-pong)
     int *count;          // [4] device counters: active[0], active[1], done, spare
     int32_t *level_iters;  // [B][YHB_MAX_LEVELS]
