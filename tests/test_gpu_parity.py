@@ -207,7 +207,7 @@ def test_engines_agree_with_golden(yb, golden, engine, peel):
     hb.engine, hb.peel = engine, peel
     res = hb.run_sweep(y, [(h['i2'], 'ac', vin / 2), (h['i4'], 'ac', vin / 2), (h['i3'], 'dc', vb), (h['i5'], 'dc', vb)])
     Nc, Wc, fused = hb._plan.core()
-    assert fused == (engine == 'auto')
+    assert fused == (engine == 'auto' and peel)      # the unpeeled 210 x 210 system does not fit one SM
     assert Wc == (84 if peel else 210)
     for k in range(len(vb)):
         its = g['iters'][k]

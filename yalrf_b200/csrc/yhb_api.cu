@@ -32,6 +32,33 @@ void set_error(const std::string &msg) { g_err = msg; }
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+struct FusedChoice {
+    bool ok;
+    int T;        // register tile (0 = core system in shared memory)
+    size_t smem;  // dynamic shared memory bytes
+};
+
+constexpr size_t kMaxEvalSmem = 200 * 1024;
+
+// which fused-engine variant runs this plan (if any)
+static FusedChoice fused_choice(const PlanDev &d) {
+    constexpr size_t lim = 227 * 1024 - 2048;  // dynamic part: the 227 KB per-CTA limit includes the static __shared__
+    FusedChoice f{false, 0, 0};
+    if (d.flags & YHB_FLAG_STAGED) return f;
+    const int T = std::max(1, (d.Wc + 1 + 15) / 16);
+    size_t b = 0;
+    switch (T) {
+#define YHB_CASE(t) case t: b = fused_smem_doubles<t>(d) * sizeof(double); break;
+        YHB_CASE(1) YHB_CASE(2) YHB_CASE(3) YHB_CASE(4) YHB_CASE(5) YHB_CASE(6) YHB_CASE(7) YHB_CASE(8)
+#undef YHB_CASE
+        default: b = 0;
+    }
+    if (b > 0 && b <= lim) return FusedChoice{true, T, b};
+    b = fused_smem_doubles<0>(d) * sizeof(double);
+    if (b <= lim) return FusedChoice{true, 0, b};
+    return f;
+}
+
 // ---- optional per-kernel timing ---------------------------------------------------------------------
 enum { PK_PREPARE = 0, PK_DC, PK_INIT, PK_EVAL, PK_ASSEMBLE, PK_LU, PK_FINISH, PK_FUSED };
 struct Prof {
@@ -347,9 +374,12 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
             for (int n = 0; n < N; ++n) {  // row singletons
                 if (!act_row[n]) continue;
                 int cnt = 0, last = -1;
-                for (int p : row_cols[n])
+                bool linear_row = true;  // an ideal-source row carries no nonlinear block
+                for (int p : row_cols[n]) {
+                    if (p < d.npair_nl) linear_row = false;
                     if (!a_known[pairs[p].second]) { ++cnt; last = p; }
-                if (cnt == 1 && unit_sign[last] != 0 && act_col[pairs[last].second]) {
+                }
+                if (linear_row && cnt == 1 && unit_sign[last] != 0 && act_col[pairs[last].second]) {
                     a_row.push_back(n);
                     a_col.push_back(pairs[last].second);
                     a_sgn.push_back(unit_sign[last]);
@@ -362,9 +392,12 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
             for (int m = 0; m < N; ++m) {  // column singletons
                 if (!act_col[m]) continue;
                 int cnt = 0, last = -1;
-                for (int p : col_rows[m])
+                bool linear_col = true;  // the recovered unknown (a source current) feeds no nonlinear block
+                for (int p : col_rows[m]) {
+                    if (p < d.npair_nl) linear_col = false;
                     if (act_row[pairs[p].first]) { ++cnt; last = p; }
-                if (cnt == 1 && unit_sign[last] != 0) {
+                }
+                if (linear_col && cnt == 1 && unit_sign[last] != 0) {
                     b_row.push_back(pairs[last].first);
                     b_col.push_back(m);
                     b_sgn.push_back(unit_sign[last]);
@@ -503,7 +536,7 @@ extern "C" int yhb_plan_core(const yhb_plan *pl, int32_t *Nc, int32_t *Wc, int32
     if (!pl) { set_error("null plan"); return -1; }
     if (Nc) *Nc = pl->d.Nc;
     if (Wc) *Wc = pl->d.Wc;
-    if (fused) *fused = fused_smem_doubles(pl->d) * sizeof(double) <= 227 * 1024 && !(pl->d.flags & YHB_FLAG_STAGED);
+    if (fused) *fused = fused_choice(pl->d).ok;
     return 0;
 }
 
@@ -529,8 +562,6 @@ struct Carver {
     }
 };
 
-constexpr size_t kMaxEvalSmem = 200 * 1024;
-constexpr size_t kMaxFusedSmem = 227 * 1024;
 
 struct Layout {
     Workspace ws;
@@ -539,6 +570,7 @@ struct Layout {
     size_t bytes;
     bool eval_smem;
     bool fused;
+    FusedChoice fc;
 };
 
 Layout carve(const yhb_plan *pl, int B, void *base) {
@@ -565,11 +597,14 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     L.eval_smem = esd * sizeof(double) <= kMaxEvalSmem;
     ws.scratch_stride = L.eval_smem ? 0 : esd;
     ws.scratch = c.take<double>(L.eval_smem ? 1 : (size_t)B * esd);
-    L.fused = fused_smem_doubles(d) * sizeof(double) <= kMaxFusedSmem && !(d.flags & YHB_FLAG_STAGED);
+    L.fc = fused_choice(d);
+    L.fused = L.fc.ok;
     ws.j_stride = L.fused ? 0 : (size_t)d.Wc * d.Wc;
     ws.J = c.take<double>(L.fused ? 1 : (size_t)B * ws.j_stride);
-    ws.xstep = c.take<double>(L.fused ? 1 : B * W);
+    ws.x_stride = W + newton_scratch_doubles(d);
+    ws.xstep = c.take<double>(L.fused ? 1 : B * ws.x_stride);
     ws.rhs = c.take<double>(L.fused ? 1 : (size_t)B * (d.Wc + 1));
+    ws.pairwav = c.take<double>((size_t)B * std::max(d.npair_nl, 1) * 2 * S);
     ws.list[0] = c.take<int>(B);
     ws.list[1] = c.take<int>(B);
     ws.count = c.take<int>(4);
@@ -674,22 +709,26 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
     YHB_CUDA(cudaGetLastError());
     EvalArgs ea = eval_args(pl, p, opt, L);
     if (L.fused) {
-        const int fsmem = (int)(fused_smem_doubles(d) * sizeof(double));
-        static int fused_cfg = 0;
-        if (fsmem > fused_cfg) {
-            YHB_CUDA(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxFusedSmem));
-            fused_cfg = (int)kMaxFusedSmem;
-        }
-        int per_sm = 0;
-        YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused, kFusedThreads, fsmem));
+        const int fsmem = (int)L.fc.smem;
         int dev = 0, sms = 0;
         YHB_CUDA(cudaGetDevice(&dev));
         YHB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const int grid = std::min(B, std::max(1, per_sm) * sms);  // persistent CTAs pulling circuits from a queue
-        {
-            ProfScope ps(PK_FUSED, st);
-            k_fused<<<grid, kFusedThreads, fsmem, st>>>(d, ws, ea);
+        // persistent CTAs pulling circuits from a queue: grid = resident CTAs per SM x SMs
+#define YHB_LAUNCH_FUSED(t)                                                                                   \
+    case t: {                                                                                                 \
+        YHB_CUDA(cudaFuncSetAttribute(k_fused<t>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));        \
+        int per_sm = 0;                                                                                       \
+        YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<t>, kFusedThreads, fsmem));   \
+        const int grid = std::min(B, std::max(1, per_sm) * sms);                                              \
+        ProfScope ps(PK_FUSED, st);                                                                           \
+        k_fused<t><<<grid, kFusedThreads, fsmem, st>>>(d, ws, ea);                                            \
+    } break;
+        switch (L.fc.T) {
+            YHB_LAUNCH_FUSED(0) YHB_LAUNCH_FUSED(1) YHB_LAUNCH_FUSED(2) YHB_LAUNCH_FUSED(3) YHB_LAUNCH_FUSED(4)
+            YHB_LAUNCH_FUSED(5) YHB_LAUNCH_FUSED(6) YHB_LAUNCH_FUSED(7) YHB_LAUNCH_FUSED(8)
+            default: set_error("no fused kernel for this core size"); return -4;
         }
+#undef YHB_LAUNCH_FUSED
         YHB_CUDA(cudaGetLastError());
         return launch_finish(pl, L, res, st);
     }

@@ -123,7 +123,9 @@ struct Workspace {
     size_t scratch_stride;
     double *J;           // staged engine: core Jacobians [B][j_stride] (stage entry point: caller's full [B][W][W])
     size_t j_stride;
-    double *xstep;       // [B][W]  staged engine: Newton step work vector
+    double *pairwav;     // [B][npair_nl][2][S] pair conductance / capacitance waveforms (staged engine)
+    double *xstep;       // [B][x_stride]  staged engine: Newton step vector + scratch of newton_pre / newton_post
+    size_t x_stride;
     double *rhs;         // [B][Wc+1]
     int *list[2];        // [B] active-circuit lists (ping-pong)
     int *count;          // [4] device counters: active[0], active[1], done, spare
