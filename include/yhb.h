@@ -197,6 +197,9 @@ int yhb_stage_device_eval(const yhb_plan *plan, const yhb_params *p, const doubl
 int yhb_stage_assemble(const yhb_plan *plan, const yhb_params *p, void *ws, size_t ws_bytes,
                        const double *V, const double *vtprev, const double *alpha, double *cacc,
                        double *J, double *F, void *stream);
+/* the fused engine's register-tiled Gauss-Jordan solver on its own: x[B][n] = A^-1 b, A[B][n][n] row-major,
+ * 1 <= n <= 127 */
+int yhb_stage_gj(int32_t batch, int32_t n, const double *A, const double *b, double *x, void *stream);
 /* LU with partial pivoting + solve (:620-621): x[B][W] = J^-1 F; J is overwritten by its factors */
 int yhb_stage_lu(int32_t batch, int32_t W, double *J, const double *F, double *x, void *stream);
 

@@ -45,11 +45,11 @@ static FusedChoice fused_choice(const PlanDev &d) {
     constexpr size_t lim = 227 * 1024 - 2048;  // dynamic part: the 227 KB per-CTA limit includes the static __shared__
     FusedChoice f{false, 0, 0};
     if (d.flags & YHB_FLAG_STAGED) return f;
-    const int T = std::max(1, (d.Wc + 1 + 15) / 16);
+    const int T = std::max(1, (d.Wc + 1 + 31) / 32);  // register tile: T rows x 4 T columns per thread
     size_t b = 0;
     switch (T) {
 #define YHB_CASE(t) case t: b = fused_smem_doubles<t>(d) * sizeof(double); break;
-        YHB_CASE(1) YHB_CASE(2) YHB_CASE(3) YHB_CASE(4) YHB_CASE(5) YHB_CASE(6) YHB_CASE(7) YHB_CASE(8)
+        YHB_CASE(1) YHB_CASE(2) YHB_CASE(3) YHB_CASE(4)
 #undef YHB_CASE
         default: b = 0;
     }
@@ -613,7 +613,7 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.dcV = c.take<double>((size_t)B * d.N);
     ws.dcinfo = c.take<int>(2 * (size_t)B);
     const int M = d.N + pl->num_inductors;
-    ws.dc_stride = dc_scratch_doubles(M, d.nd, d.nb);
+    ws.dc_stride = dc_scratch_doubles(M, d.nd, d.nb, d.nc);
     ws.dcscratch = c.take<double>((size_t)B * ws.dc_stride);
     L.dd = c.take<DiodeDerived>((size_t)B * std::max(d.nd, 1));
     L.bd = c.take<BjtDerived>((size_t)B * std::max(d.nb, 1));
@@ -725,7 +725,6 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
     } break;
         switch (L.fc.T) {
             YHB_LAUNCH_FUSED(0) YHB_LAUNCH_FUSED(1) YHB_LAUNCH_FUSED(2) YHB_LAUNCH_FUSED(3) YHB_LAUNCH_FUSED(4)
-            YHB_LAUNCH_FUSED(5) YHB_LAUNCH_FUSED(6) YHB_LAUNCH_FUSED(7) YHB_LAUNCH_FUSED(8)
             default: set_error("no fused kernel for this core size"); return -4;
         }
 #undef YHB_LAUNCH_FUSED
@@ -796,9 +795,13 @@ extern "C" int yhb_dc_solve(const yhb_plan *pl, const yhb_params *p, void *wsbuf
     a.Vdc = Vdc ? Vdc : L.ws.dcV;
     a.info = dc_info ? dc_info : L.ws.dcinfo;
     cudaStream_t st = (cudaStream_t)stream;
+    size_t dsm = (a.M + 2) * sizeof(double);
+    a.use_smem = (dsm + a.stride * sizeof(double)) <= 40 * 1024;  // small circuits: the whole DC analysis on chip
+    if (a.use_smem) dsm += a.stride * sizeof(double);
     {
         ProfScope ps(PK_DC, st);
-        k_dc<<<p->batch, kDcThreads, (a.M + 2) * sizeof(double), st>>>(d, a, p->batch);
+        const int threads = (a.M <= 24 && a.nnl <= 32) ? 32 : kDcThreads;
+        k_dc<<<p->batch, threads, dsm, st>>>(d, a, p->batch);
     }
     YHB_CUDA(cudaGetLastError());
     return 0;
@@ -1027,6 +1030,23 @@ extern "C" int yhb_stage_assemble(const yhb_plan *pl, const yhb_params *p, void 
     k_eval<<<p->batch, kEvalThreads, smem, st>>>(d, L.ws, ea);
     dim3 ga(p->batch, (d.W + kAsmRows - 1) / kAsmRows);
     k_assemble<<<ga, 256, 0, st>>>(d, L.ws, ea);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int yhb_stage_gj(int32_t batch, int32_t n, const double *A, const double *F, double *x, void *stream) {
+    if (batch < 1 || n < 1 || n > 127 || !A || !F || !x) { set_error("bad argument (1 <= n <= 127)"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = (n + 1 + 31) / 32;
+    switch (T) {
+#define YHB_CASE(t)                                                                                         \
+    case t: {                                                                                               \
+        size_t smem = (sizeof(GjBufs<t>) + 7) / 8 * 8 + (size_t)(n + 1) * sizeof(double);                   \
+        k_gj_stage<t><<<batch, 256, smem, st>>>(batch, n, A, F, x);                                         \
+    } break;
+        YHB_CASE(1) YHB_CASE(2) YHB_CASE(3) YHB_CASE(4)
+#undef YHB_CASE
+    }
     YHB_CUDA(cudaGetLastError());
     return 0;
 }

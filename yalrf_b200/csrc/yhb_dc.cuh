@@ -10,7 +10,7 @@
 
 namespace yhb {
 
-constexpr int kDcThreads = 128;
+constexpr int kDcThreads = 128;  // upper bound; tiny circuits run one warp per circuit
 
 struct DcArgs {
     const double *lin_val, *src_val, *diode_par, *bjt_par, *cubic_par;
@@ -19,14 +19,17 @@ struct DcArgs {
     const int *nl_index;   // [nnl]
     int nnl;
     int M;                 // unknowns: N node voltages + one branch current per inductor
-    double *scratch;       // [B][stride]
+    double *scratch;       // [B][stride] (used when the per-circuit scratch does not fit shared memory)
     size_t stride;
+    int use_smem;
     double *Vdc;           // [B][N]
     int *info;             // [B][2] converged, Newton iterations
 };
 
-__host__ __device__ inline size_t dc_scratch_doubles(int M, int nd, int nb) {
-    return (size_t)3 * M * M + (size_t)7 * M + 3 * nd + 2 * nb + 8;
+constexpr int kDcOut = 12;  // per-device stamp values handed from the parallel evaluation to the ordered stamping
+
+__host__ __device__ inline size_t dc_scratch_doubles(int M, int nd, int nb, int nc) {
+    return (size_t)3 * M * M + (size_t)7 * M + 3 * nd + 2 * nb + (size_t)kDcOut * (nd + nb + nc) + 8;
 }
 
 struct DcCtx {
@@ -34,7 +37,7 @@ struct DcCtx {
     const DcArgs *a;
     int b, M;
     double *A, *Anl, *Aw, *z, *zs, *znl, *zw, *xk, *x, *xprev, *x0;
-    double *dst, *bst;
+    double *dst, *bst, *dout;
     double *s_row, *s_val;
     int *s_idx;
     int *s_flag;
@@ -61,12 +64,14 @@ __device__ inline void dc_stamp2(double *A, double *z, int M, int n1, int n2, do
     if (n2 > 0) z[n2 - 1] = z[n2 - 1] + I;
 }
 
-// nonlinear stamps of every device at xk into (Anl, znl), thread 0 only
-__device__ inline void dc_stamp_nonlinear(DcCtx &c, const double *xk) {
+// Device evaluation at xk, one thread per device (the limiter state of a device is private to it); the stamp
+// values go to dout, and dc_apply_stamps adds them into (Anl, znl) in netlist order.
+__device__ inline void dc_eval_devices(DcCtx &c, const double *xk) {
     const PlanDev &P = *c.P;
-    const int M = c.M, b = c.b;
-    for (int t = 0; t < c.a->nnl; ++t) {
+    const int b = c.b;
+    for (int t = threadIdx.x; t < c.a->nnl; t += blockDim.x) {
         const int kind = c.a->nl_kind[t], idx = c.a->nl_index[t];
+        double *o = c.dout + (size_t)kDcOut * t;
         if (kind == 0) {  // Diode.calc_dc + add_dc_stamps, Diode.py:98-116, :238-294
             const double *p = c.a->diode_par + ((size_t)b * P.nd + idx) * YHB_DIODE_NPAR;
             double *st = c.dst + 3 * idx;  // Vdold, It, gt
@@ -97,7 +102,8 @@ __device__ inline void dc_stamp_nonlinear(DcCtx &c, const double *xk) {
             double gd = gdf + gdr + gbr + (1e-12);
             st[1] = (Id - gd * Vd) / (1. + gd * Rs);
             st[2] = gd / (1. + gd * Rs);
-            dc_stamp2(c.Anl, c.znl, M, n1, n2, st[2], st[1]);
+            o[0] = st[2];
+            o[1] = st[1];
         } else if (kind == 1) {  // BJT.calc_dc + add_dc_stamps, BJT.py:134-167, :319-416 (honours self.type)
             const double *p = c.a->bjt_par + ((size_t)b * P.nb + idx) * YHB_BJT_NPAR;
             double *st = c.bst + 2 * idx;  // Vbeold, Vbcold
@@ -140,21 +146,19 @@ __device__ inline void dc_stamp_nonlinear(DcCtx &c, const double *xk) {
             double Ibeeq = Ibe - gpi * Vbe;
             double Ibceq = Ibc - gmu * Vbc;
             double Iceeq = It - gmf * Vbe - gmr * Vbc;
-            double *A = c.Anl, *z = c.znl;
-#define YHB_A(r, cc, v) do { if ((r) > 0 && (cc) > 0) A[(size_t)((r) - 1) * M + ((cc) - 1)] += (v); } while (0)
-            YHB_A(B, B, gmu + gpi);
-            YHB_A(B, C, -gmu);
-            YHB_A(B, E, -gpi);
-            YHB_A(C, B, -gmu + gmf + gmr);
-            YHB_A(C, C, gmu - gmr);
-            YHB_A(C, E, -gmf);
-            YHB_A(E, B, -gpi - gmf - gmr);
-            YHB_A(E, C, gmr);
-            YHB_A(E, E, gpi + gmf);
-#undef YHB_A
-            if (B > 0) z[B - 1] = z[B - 1] + (-Ibeeq - Ibceq) * type;
-            if (C > 0) z[C - 1] = z[C - 1] + (+Ibceq - Iceeq) * type;
-            if (E > 0) z[E - 1] = z[E - 1] + (+Ibeeq + Iceeq) * type;
+            o[0] = gmu + gpi;
+            o[1] = -gmu;
+            o[2] = -gpi;
+            o[3] = -gmu + gmf + gmr;
+            o[4] = gmu - gmr;
+            o[5] = -gmf;
+            o[6] = -gpi - gmf - gmr;
+            o[7] = gmr;
+            o[8] = gpi + gmf;
+            o[9] = (-Ibeeq - Ibceq) * type;
+            o[10] = (+Ibceq - Iceeq) * type;
+            o[11] = (+Ibeeq + Iceeq) * type;
+            (void)B; (void)C; (void)E;
         } else {  // CubicNonLinearity.add_dc_stamps, CubicNonLinearity.py:20-34 (g = 3 alpha V^2 here)
             const double alpha = c.a->cubic_par[(size_t)b * P.nc + idx];
             const int n1 = P.cubic_nodes[2 * idx], n2 = P.cubic_nodes[2 * idx + 1];
@@ -162,17 +166,51 @@ __device__ inline void dc_stamp_nonlinear(DcCtx &c, const double *xk) {
             double g = 3 * alpha * V * V;
             double I = alpha * V * V * V;
             double Ieq = I - g * V;
-            dc_stamp2(c.Anl, c.znl, M, n1, n2, g, Ieq);
+            o[0] = g;
+            o[1] = Ieq;
+        }
+    }
+}
+
+// stamps of every device into (Anl, znl) in netlist order (fixes the summation order), thread 0 only
+__device__ inline void dc_apply_stamps(DcCtx &c) {
+    const PlanDev &P = *c.P;
+    const int M = c.M;
+    double *A = c.Anl, *z = c.znl;
+    for (int t = 0; t < c.a->nnl; ++t) {
+        const int kind = c.a->nl_kind[t], idx = c.a->nl_index[t];
+        const double *o = c.dout + (size_t)kDcOut * t;
+        if (kind == 0) {
+            dc_stamp2(A, z, M, P.diode_nodes[2 * idx], P.diode_nodes[2 * idx + 1], o[0], o[1]);
+        } else if (kind == 2) {
+            dc_stamp2(A, z, M, P.cubic_nodes[2 * idx], P.cubic_nodes[2 * idx + 1], o[0], o[1]);
+        } else {
+            const int B = P.bjt_nodes[3 * idx], C = P.bjt_nodes[3 * idx + 1], E = P.bjt_nodes[3 * idx + 2];
+#define YHB_A(r, cc, v) do { if ((r) > 0 && (cc) > 0) A[(size_t)((r) - 1) * M + ((cc) - 1)] += (v); } while (0)
+            YHB_A(B, B, o[0]);
+            YHB_A(B, C, o[1]);
+            YHB_A(B, E, o[2]);
+            YHB_A(C, B, o[3]);
+            YHB_A(C, C, o[4]);
+            YHB_A(C, E, o[5]);
+            YHB_A(E, B, o[6]);
+            YHB_A(E, C, o[7]);
+            YHB_A(E, E, o[8]);
+#undef YHB_A
+            if (B > 0) z[B - 1] = z[B - 1] + o[9];
+            if (C > 0) z[C - 1] = z[C - 1] + o[10];
+            if (E > 0) z[E - 1] = z[E - 1] + o[11];
         }
     }
 }
 
 // Diode.check_vlimit (Diode.py:296-313) / BJT.check_vlimit (BJT.py:418-436) on the NEW solution; both
-// advance the limiter state.  Thread 0 only.  Every device is visited (no early exit), as in DC.py:176-179.
+// advance the limiter state.  One thread per device; every device is visited (no early exit), as in DC.py:176-179.
+// Returns this thread's partial verdict (combine with __syncthreads_and).
 __device__ inline bool dc_check_vlimit(DcCtx &c, const double *x, double vabstol) {
     const PlanDev &P = *c.P;
     bool ok = true;
-    for (int t = 0; t < c.a->nnl; ++t) {
+    for (int t = threadIdx.x; t < c.a->nnl; t += blockDim.x) {
         const int kind = c.a->nl_kind[t], idx = c.a->nl_index[t];
         if (kind == 0) {
             const double *p = c.a->diode_par + ((size_t)c.b * P.nd + idx) * YHB_DIODE_NPAR;
@@ -215,7 +253,9 @@ __device__ inline bool dc_newton(DcCtx &c, double extra_g, double zscale, const 
         for (int i = tid; i < M * M; i += nt) c.Anl[i] = 0.;
         for (int i = tid; i < M; i += nt) c.znl[i] = 0.;
         __syncthreads();
-        if (tid == 0) dc_stamp_nonlinear(c, c.xk);
+        dc_eval_devices(c, c.xk);
+        __syncthreads();
+        if (tid == 0) dc_apply_stamps(c);
         __syncthreads();
         for (int i = tid; i < M * M; i += nt) {
             int r = i / M, cc = i - r * M;
@@ -230,17 +270,11 @@ __device__ inline bool dc_newton(DcCtx &c, double extra_g, double zscale, const 
         int nan = 0;
         for (int i = tid; i < M; i += nt) nan |= isnan(c.x[i]);
         if (__syncthreads_or(nan)) return false;  // Solver.py:14
-        if (tid == 0) {
-            bool vconv = true, iconv = true;
-            for (int i = 0; i < N; ++i)
-                if (fabs(c.x[i] - c.xk[i]) > reltol * fabs(c.xk[i]) + vabstol) vconv = false;
-            for (int i = N; i < M; ++i)
-                if (fabs(c.x[i] - c.xk[i]) > reltol * fabs(c.xk[i]) + iabstol) iconv = false;
-            bool vlim = dc_check_vlimit(c, c.x, vabstol);
-            *c.s_flag = vconv && iconv && vlim;
-        }
-        __syncthreads();
-        converged = *c.s_flag != 0;
+        bool okc = true;
+        for (int i = tid; i < M; i += nt)
+            if (fabs(c.x[i] - c.xk[i]) > reltol * fabs(c.xk[i]) + (i < N ? vabstol : iabstol)) okc = false;
+        bool vlim = dc_check_vlimit(c, c.x, vabstol);
+        converged = __syncthreads_and(okc && vlim) != 0;
         if (!converged) {
             for (int i = tid; i < M; i += nt) c.xk[i] = c.x[i];
             k = k + 1;
@@ -263,7 +297,7 @@ __global__ void __launch_bounds__(kDcThreads) k_dc(PlanDev P, DcArgs a, int batc
     c.a = &a;
     c.b = b;
     c.M = M;
-    double *sc = a.scratch + (size_t)b * a.stride;
+    double *sc = a.use_smem ? s_row + (M + 2) : a.scratch + (size_t)b * a.stride;
     c.A = sc;
     c.Anl = c.A + (size_t)M * M;
     c.Aw = c.Anl + (size_t)M * M;
@@ -276,6 +310,7 @@ __global__ void __launch_bounds__(kDcThreads) k_dc(PlanDev P, DcArgs a, int batc
     c.x0 = c.xprev + M;
     c.dst = c.x0 + M;
     c.bst = c.dst + 3 * P.nd;
+    c.dout = c.bst + 2 * P.nb;
     c.s_row = s_row;
     c.s_val = s_val;
     c.s_idx = s_idx;
