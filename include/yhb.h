@@ -169,7 +169,9 @@ int yhb_dc_solve(const yhb_plan *plan, const yhb_params *p, void *ws, size_t ws_
 
 /* run() (:234-405): optional direct attempt from V0, then the source-stepping ladder (:338-384) from
  * the DC point; every hb_loop (:407-631) runs on the GPU.  have_v0 != 0: res->V holds the start.
- * Vdc[B][N]: DC node voltages (from yhb_dc_solve), used for cold starts and after a failed direct attempt. */
+ * Vdc[B][N]: DC node voltages (from yhb_dc_solve), used for cold starts and after a failed direct attempt; with
+ * have_v0 it may be NULL, and a circuit whose direct attempt fails then reports converged = -1 ("needs the DC
+ * point": solve again from the same V0 with Vdc). */
 int yhb_solve(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt, void *ws,
               size_t ws_bytes, int32_t have_v0, const double *Vdc, const yhb_result *res, void *stream);
 

@@ -255,3 +255,42 @@ def test_warm_start_failure_falls_back_to_ladder(yb):
     assert hb.last.levels() == [l[1] for l in o.level_log]
     if conv:
         assert relmax(hb.V, o.V) < 1e-9
+
+
+# ----------------------------------------------------------------------------- config 2: oscillators
+def test_peltz_oscillator(yb, golden, capsys):
+    """README / tests/HBOsc_Peltz.py: run_oscillator on the Peltz oscillator, K = 10.  fosc, Vosc and the phasors of
+    the unmodified reference (tests/golden/peltz_osc.npz); print_v text format (:112-118)."""
+    g = golden('peltz_osc')
+    y = yb.Netlist('Oscillator')
+    h = circuits.peltz(y)
+    hb = mthb('HB1')
+    hb.options['maxiter'] = 100
+    conv, freqs, Vf, _, _ = hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node'])
+    assert conv
+    assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 1e-9
+    assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 1e-9
+    assert abs(hb.freq - float(g['fosc'])) / float(g['fosc']) < 1e-9          # result also in hb.freq
+    nb = y.get_node_idx('nb') - 1
+    assert relmax(Vf[nb], g['Vf'][nb]) < 1e-9
+    for n in range(4):                                                      # circuit nodes; the probe-current node: see test_peltz_probe_fixed
+        assert np.max(np.abs(Vf[n] - g['Vf'][n])) < 1e-8 * np.max(np.abs(g['Vf']))
+    # the GPU answer evaluated by the reference's own objective definition is at the quantisation floor
+    n1, n2 = hb.get_node_idx('nb'), hb.get_node_idx('HB1.nosc2')
+    assert abs((Vf[n1, 1] - Vf[n2, 1]) * 1e9 / Vf[n1, 1]) < 1e-6
+    hb.print_v('nb')
+    out = capsys.readouterr().out
+    assert 'Voltage at node: nb' in out and 'Freq [Hz]\tVmag [V]\tPhase [°]' in out
+    assert 'Frequency of oscillation = ' in out and 'Oscillation amplitude = ' in out
+
+
+def test_vanderpol_oscillator(yb, golden):
+    """tests/HBOsc_VanDerPol.py: cubic nonlinearity, inductor / capacitor / negative resistor, K = 20."""
+    g = golden('vanderpol_osc')
+    y = yb.Netlist('vdp')
+    h = circuits.vanderpol(y)
+    hb = mthb('HB1')
+    conv, freqs, Vf, _, _ = hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node'])
+    assert conv
+    assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 1e-8
+    assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 1e-8

@@ -31,6 +31,7 @@ class MultiToneHarmonicBalance:
         self.verbose = False          # print the reference's per-level log lines (:354, :358, :383-384, :597-598)
         self.engine = 'auto'          # 'auto': fused on-chip engine when the circuit fits one SM; 'staged': HBM Jacobian
         self.peel = True              # eliminate ideal-source rows symbolically before the dense factorisation
+        self.distributed = False      # run_batch / run_sweep: shard the circuits over torch.distributed ranks, gather
         self.last = None              # BatchResult of the last call
 
     # ------------------------------------------------------------------ helpers
@@ -130,12 +131,81 @@ class MultiToneHarmonicBalance:
 
     def _run_block(self, plan, pb, V0):
         self._had_v0 = V0 is not None
-        res = E.run_host(plan, pb, self.options, V0)
+        if self.distributed:
+            from .._dist import run_block_distributed
+            res = run_block_distributed(plan, pb, self.options, V0)
+        else:
+            res = E.run_host(plan, pb, self.options, V0)
         res.freqs = self._freqs(plan)
         if self.num_tones == 2:
             res.freqs = np.abs(res.freqs)
         self.last = res
         return res
+
+    # ------------------------------------------------------------------ oscillator (:137-232)
+    def run_oscillator(self, netlist, f0, numharmonics, V0, node, useprev=False):
+        """Autonomous-oscillator analysis with the reference's formulation: an oscillator probe (AC current source
+        + gyrator = voltage source, in series with an IdealHarmonicFilter that is a short only at the fundamental)
+        and Nelder-Mead on (fosc, Vosc) minimising |Yosc| = |probe current / probe voltage| (:182-196).  Every
+        objective evaluation is one warm-started GPU solve.  Same arguments, prints and return value as the
+        reference; the optimiser call is the reference's own (scipy.optimize.fmin, :204-212)."""
+        from scipy import optimize
+        netlist = netlist.copy()
+        self.freq = f0
+        self.numharmonics = numharmonics
+        Voscprobe = netlist.add_iac(self.name + '.I.Oscprobe', self.name + '.nosc1', 'gnd', ac=V0, freq=f0)
+        netlist.add_gyrator(self.name + '.G.Oscprobe', self.name + '.nosc1', self.name + '.nosc2', 'gnd', 'gnd', 1)
+        Zoscprobe = netlist.add_idealharmonicfilter(self.name + 'IHF.Oscprobe', self.name + '.nosc2', node, f0)
+        self.osc_evals = []
+
+        class SmallEnoughException(Exception):
+            pass
+
+        def objFunc(x, info):
+            fosc = float(x[0])
+            Vosc = float(x[1])
+            Voscprobe.ac = Vosc
+            Voscprobe.freq = fosc
+            Zoscprobe.freq = fosc
+            self.freq = fosc
+            if info['itercnt'] > 0 or info['useprev']:
+                converged, freqs, Vf, _, _ = self.run(netlist, self.V)
+            else:
+                converged, freqs, Vf, _, _ = self.run(netlist)
+            if not converged:
+                self.osc_evals.append((fosc, Vosc, 1e2))
+                return 1e2
+            n1 = self.get_node_idx(info['osc_node'])
+            n2 = self.get_node_idx(self.name + '.nosc2')
+            Voscx = Vf[n1, 1]
+            Iosc = (Vf[n1, 1] - Vf[n2, 1]) * Zoscprobe.g
+            Yosc = Iosc / Voscx
+            info['itercnt'] += 1
+            self.osc_evals.append((fosc, Vosc, abs(Yosc)))
+            if self.verbose:
+                print('\nIter\tFreq [Hz]\tVosc [V]\tmag(Yosc)')
+                print('{}\t{:.8f}\t{:.8f}\t{:.2e}\n'.format(info['itercnt'], fosc, Vosc, abs(Yosc)))
+            if abs(Yosc) < 1e-12:
+                info['result'] = x
+                raise SmallEnoughException()
+            return abs(Yosc)
+
+        args = ({'itercnt': 0, 'osc_node': node, 'result': 0, 'useprev': useprev},)
+        try:
+            xopt = optimize.fmin(func=objFunc, x0=[f0, V0], args=args, xtol=1e-12, ftol=1e-12, maxfun=300,
+                                 disp=self.verbose, retall=False, full_output=True)[0]
+        except SmallEnoughException:
+            xopt = args[0]['result']
+        fosc, Vosc = float(xopt[0]), float(xopt[1])
+        Voscprobe.ac = Vosc
+        Voscprobe.freq = fosc
+        Zoscprobe.freq = fosc
+        self.freq = fosc
+        self.fosc, self.Vosc = fosc, Vosc
+        out = self.run(netlist, self.V)
+        print('Frequency of oscillation = {} Hz'.format(fosc))
+        print('Oscillation amplitude = {} V'.format(Vosc))
+        return out
 
     # ------------------------------------------------------------------ post-processing (:112-135)
     def print_v(self, node):

@@ -190,6 +190,7 @@ class DeviceBatch:
         self.err = torch.zeros(B, dtype=f64, device=self.dev)
         self.Vdc = torch.zeros((B, plan.N), dtype=f64, device=self.dev)
         self.dcinfo = torch.zeros((B, 2), dtype=i32, device=self.dev)
+        self.dc_done = False
         self.ws_bytes = L.lib().yhb_workspace_bytes(plan.handle, B)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev)
         r = L.Result()
@@ -209,5 +210,7 @@ class DeviceBatch:
         if not have_v0:
             L.check(lib.yhb_dc_solve(self.plan.handle, C.byref(self.params), self.ws.data_ptr(), self.ws_bytes,
                                      self.Vdc.data_ptr(), self.dcinfo.data_ptr(), st))
+            self.dc_done = True
         L.check(lib.yhb_solve(self.plan.handle, C.byref(self.params), C.byref(o), self.ws.data_ptr(), self.ws_bytes,
-                              1 if have_v0 else 0, self.Vdc.data_ptr(), C.byref(self.result), st))
+                              1 if have_v0 else 0, self.Vdc.data_ptr() if self.dc_done else None,
+                              C.byref(self.result), st))

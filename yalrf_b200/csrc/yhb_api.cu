@@ -815,9 +815,10 @@ static int solve_common(const yhb_plan *pl, const yhb_params *p, const yhb_optio
     Layout L = carve(pl, p->batch, wsbuf);
     if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
     if (have_v0 && !res->V) { set_error("have_v0 set but res->V is null"); return -1; }
-    if (!have_v0 && !Vdc && !alpha) { set_error("cold start needs Vdc"); return -1; }
+    if (!have_v0 && !Vdc) { set_error("cold start needs Vdc"); return -1; }
     if (res->V) L.ws.V = res->V;
     if (Vdc) L.ws.dcV = const_cast<double *>(Vdc);
+    L.ws.dc_valid = Vdc != nullptr;
     std::lock_guard<std::mutex> lk(const_cast<yhb_plan *>(pl)->mu);  // pinned counter buffer is per plan
     return run_loop(pl, p, opt, L, have_v0, alpha, res, (cudaStream_t)stream);
 }
@@ -891,9 +892,25 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
     H2D(dp.cubic_par, hp->cubic_par, B * d.nc);
     if (V0) H2D(dr.V, V0, B * W);
 #undef H2D
-    if (int rc = yhb_dc_solve(pl, &dp, wsb, wsbytes, nullptr, nullptr, st)) return rc;
     Layout L = carve(pl, (int)B, wsb);
-    if (int rc = yhb_solve(pl, &dp, opt, wsb, wsbytes, V0 != nullptr, L.ws.dcV, &dr, st)) return rc;
+    if (!V0) {  // cold start: DC operating points first (calc_V0, :321-322)
+        if (int rc = yhb_dc_solve(pl, &dp, wsb, wsbytes, nullptr, nullptr, st)) return rc;
+        if (int rc = yhb_solve(pl, &dp, opt, wsb, wsbytes, 0, L.ws.dcV, &dr, st)) return rc;
+    } else {
+        // warm start: the DC analysis is only needed if a direct attempt fails (:333-335); such circuits come
+        // back with converged = -1 and the batch is re-run from the same V0 with the DC points available
+        if (int rc = yhb_solve(pl, &dp, opt, wsb, wsbytes, 1, nullptr, &dr, st)) return rc;
+        std::vector<int32_t> conv(B);
+        YHB_CUDA(cudaMemcpyAsync(conv.data(), dr.converged, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        YHB_CUDA(cudaStreamSynchronize(st));
+        bool need_dc = false;
+        for (size_t i = 0; i < B; ++i) need_dc = need_dc || conv[i] < 0;
+        if (need_dc) {
+            YHB_CUDA(cudaMemcpyAsync(dr.V, V0, B * W * sizeof(double), cudaMemcpyHostToDevice, st));
+            if (int rc = yhb_dc_solve(pl, &dp, wsb, wsbytes, nullptr, nullptr, st)) return rc;
+            if (int rc = yhb_solve(pl, &dp, opt, wsb, wsbytes, 1, L.ws.dcV, &dr, st)) return rc;
+        }
+    }
 #define D2H(dst, src, cnt)                                                                              \
     do {                                                                                                \
         if (dst) YHB_CUDA(cudaMemcpyAsync((dst), (src), (cnt) * sizeof(*(dst)), cudaMemcpyDeviceToHost, st)); \

@@ -118,6 +118,7 @@ struct Workspace {
     double *omega;       // [B][K+1]
     int *negbin;         // [B][K+1] real frequency of the bin is negative (two-tone, :725)
     int stage_first;     // stage entry points: treat the evaluation as the first of an hb_loop
+    int dc_valid;        // dcV holds DC operating points (needed for cold starts and after a failed direct attempt)
     double *Is;          // [B][W]  unscaled source vector (:647-684)
     double *scratch;     // [B][scratch_stride] evaluation scratch when it does not fit shared memory
     size_t scratch_stride;
