@@ -32,6 +32,49 @@ __host__ __device__ inline size_t dc_scratch_doubles(int M, int nd, int nb, int 
     return (size_t)3 * M * M + (size_t)7 * M + 3 * nd + 2 * nb + (size_t)kDcOut * (nd + nb + nc) + 8;
 }
 
+// Gaussian elimination with partial pivoting on [A | rhs] by ONE warp, n <= 32: rows live on lanes during the
+// elimination (each lane walks its own row), columns live on lanes during the row interchange.  Same pivot rule
+// and arithmetic as block_ge_solve (dgetf2-style reciprocal scaling); only __syncwarp, no block barrier.
+__device__ inline void warp_ge_solve(double *A, int lda, double *rhs, double *x, int n) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < n; ++k) {
+        const double v = (lane >= k && lane < n) ? fabs(A[(size_t)lane * lda + k]) : -1.;
+        const unsigned long long bits = v < 0. ? 0ull : (unsigned long long)__double_as_longlong(v);
+        const bool valid = lane >= k && lane < n;
+        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+        int p = __reduce_min_sync(0xffffffffu, (valid && hi == mhi && lo == mlo) ? lane : 0x7fffffff);
+        if (p == 0x7fffffff) p = k;
+        if (p != k) {
+            for (int j = k + lane; j <= n; j += 32) {
+                double *pk = (j < n) ? &A[(size_t)k * lda + j] : &rhs[k];
+                double *pp = (j < n) ? &A[(size_t)p * lda + j] : &rhs[p];
+                const double t = *pk;
+                *pk = *pp;
+                *pp = t;
+            }
+        }
+        __syncwarp();
+        const double rinv = 1. / A[(size_t)k * lda + k];
+        if (lane > k && lane < n) {
+            double *ai = A + (size_t)lane * lda;
+            const double *ak = A + (size_t)k * lda;
+            const double l = -(ai[k] * rinv);
+            for (int j = k + 1; j < n; ++j) ai[j] = fma(l, ak[j], ai[j]);
+            rhs[lane] = fma(l, rhs[k], rhs[lane]);
+        }
+        __syncwarp();
+    }
+    for (int j = n - 1; j >= 0; --j) {
+        const double xj = rhs[j] / A[(size_t)j * lda + j];
+        __syncwarp();
+        if (lane < j) rhs[lane] = fma(-A[(size_t)lane * lda + j], xj, rhs[lane]);
+        if (lane == 0) x[j] = xj;
+        __syncwarp();
+    }
+}
+
 struct DcCtx {
     const PlanDev *P;
     const DcArgs *a;
@@ -265,7 +308,12 @@ __device__ inline bool dc_newton(DcCtx &c, double extra_g, double zscale, const 
         }
         for (int i = tid; i < M; i += nt) c.zw[i] = zscale * c.z[i] + c.znl[i];
         __syncthreads();
-        block_ge_solve(c.Aw, M, c.zw, c.x, M, c.s_row, c.s_val, c.s_idx);
+        if (nt == 32) {
+            warp_ge_solve(c.Aw, M, c.zw, c.x, M);
+            __syncthreads();
+        } else {
+            block_ge_solve(c.Aw, M, c.zw, c.x, M, c.s_row, c.s_val, c.s_idx);
+        }
         c.newton += 1;
         int nan = 0;
         for (int i = tid; i < M; i += nt) nan |= isnan(c.x[i]);
