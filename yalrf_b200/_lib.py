@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libyhb.so')
+LIB_PATH = os.environ.get('YHB_LIB', os.path.join(_HERE, 'libyhb.so'))  # YHB_LIB: A/B builds of the same ABI
 
 # enums of include/yhb.h
 LIN_RESISTOR, LIN_CAPACITOR, LIN_INDUCTOR, LIN_GYRATOR, LIN_IHF = range(5)
