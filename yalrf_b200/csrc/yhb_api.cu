@@ -944,53 +944,63 @@ __global__ void k_stage_ifft(PlanDev P, int batch, const double *V, double *vt) 
     }
 }
 
-// Stand-alone device sweep (:441-570): HBM in (vt, vtprev samples + raw model parameters), HBM out
-// (model outputs per sample).  One CTA per circuit; constants are derived once per device in shared memory.
-__global__ void __launch_bounds__(256) k_stage_device_eval(PlanDev P, int batch, const double *diode_par,
-                                                           const double *bjt_par, const double *cubic_par,
-                                                           const double *vt, const double *vtprev, double *diode_out,
-                                                           double *bjt_out, double *cubic_out) {
+// Stand-alone device sweep (:441-570): HBM in (vt, vtprev samples + raw model parameters), HBM out (model outputs
+// per sample).  Persistent CTAs walk chunks of kDevChunk circuits: the hoisted model constants of the chunk are
+// derived into shared memory by one thread per (circuit, device), then one thread per (circuit, device, sample)
+// evaluates; loads and stores are contiguous along the sample index.
+constexpr int kDevChunk = 16;
+
+__global__ void __launch_bounds__(256, 2) k_stage_device_eval(PlanDev P, int batch, const double *diode_par,
+                                                              const double *bjt_par, const double *cubic_par,
+                                                              const double *vt, const double *vtprev, double *diode_out,
+                                                              double *bjt_out, double *cubic_out) {
     extern __shared__ double sm[];
-    const int b = blockIdx.x;
-    if (b >= batch) return;
     DiodeDerived *dd = reinterpret_cast<DiodeDerived *>(sm);
-    BjtDerived *bd = reinterpret_cast<BjtDerived *>(dd + P.nd);
-    for (int i = threadIdx.x; i < P.nd; i += blockDim.x)
-        diode_derive(diode_par + ((size_t)b * P.nd + i) * YHB_DIODE_NPAR, dd[i]);
-    for (int i = threadIdx.x; i < P.nb; i += blockDim.x)
-        bjt_derive(bjt_par + ((size_t)b * P.nb + i) * YHB_BJT_NPAR, P.flags, bd[i]);
-    __syncthreads();
-    const int S = P.S;
-    const double *v = vt + (size_t)b * P.W, *vo = vtprev + (size_t)b * P.W;
-    const int nitem = (P.nd + P.nc + P.nb) * S;
-    for (int it = threadIdx.x; it < nitem; it += blockDim.x) {
-        int dev = it / S, s = it - dev * S;
-        if (dev < P.nd + P.nc) {
-            const int *nodes = (dev < P.nd) ? P.diode_nodes + 2 * dev : P.cubic_nodes + 2 * (dev - P.nd);
-            int n1 = nodes[0] - 1, n2 = nodes[1] - 1;
-            double vd = (n1 >= 0 ? v[n1 * S + s] : 0.) - (n2 >= 0 ? v[n2 * S + s] : 0.);
-            double vdold = (n1 >= 0 ? vo[n1 * S + s] : 0.) - (n2 >= 0 ? vo[n2 * S + s] : 0.);
-            double g, I;
-            double *o;
-            if (dev < P.nd) {
-                diode_eval(dd[dev], vd, vdold, g, I);
-                o = diode_out + ((size_t)b * P.nd + dev) * 2 * S + s;
+    BjtDerived *bd = reinterpret_cast<BjtDerived *>(dd + (size_t)kDevChunk * P.nd);
+    const int S = P.S, W = P.W;
+    const int ndev = P.nd + P.nc + P.nb;
+    const int per = ndev * S;
+    for (int c0 = blockIdx.x * kDevChunk; c0 < batch; c0 += gridDim.x * kDevChunk) {
+        const int nc = min(kDevChunk, batch - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc * P.nd; i += blockDim.x)
+            diode_derive(diode_par + ((size_t)c0 * P.nd + i) * YHB_DIODE_NPAR, dd[i]);
+        for (int i = threadIdx.x; i < nc * P.nb; i += blockDim.x)
+            bjt_derive(bjt_par + ((size_t)c0 * P.nb + i) * YHB_BJT_NPAR, P.flags, bd[i]);
+        __syncthreads();
+        for (int it = threadIdx.x; it < nc * per; it += blockDim.x) {
+            const int cl = it / per, r = it - cl * per;
+            const int dev = r / S, s = r - dev * S;
+            const size_t b = (size_t)c0 + cl;
+            const double *v = vt + b * W, *vo = vtprev + b * W;
+            if (dev < P.nd + P.nc) {
+                const int *nodes = (dev < P.nd) ? P.diode_nodes + 2 * dev : P.cubic_nodes + 2 * (dev - P.nd);
+                int n1 = nodes[0] - 1, n2 = nodes[1] - 1;
+                double vd = (n1 >= 0 ? v[n1 * S + s] : 0.) - (n2 >= 0 ? v[n2 * S + s] : 0.);
+                double vdold = (n1 >= 0 ? vo[n1 * S + s] : 0.) - (n2 >= 0 ? vo[n2 * S + s] : 0.);
+                double g, I;
+                double *o;
+                if (dev < P.nd) {
+                    diode_eval(dd[cl * P.nd + dev], vd, vdold, g, I);
+                    o = diode_out + (b * P.nd + dev) * 2 * S + s;
+                } else {
+                    cubic_eval(cubic_par[b * P.nc + dev - P.nd], vd, g, I);
+                    o = cubic_out + (b * P.nc + dev - P.nd) * 2 * S + s;
+                }
+                o[0] = g;
+                o[S] = I;
             } else {
-                cubic_eval(cubic_par[(size_t)b * P.nc + dev - P.nd], vd, g, I);
-                o = cubic_out + ((size_t)b * P.nc + dev - P.nd) * 2 * S + s;
-            }
-            o[0] = g;
-            o[S] = I;
-        } else {
-            int q = dev - P.nd - P.nc;
-            const int *nodes = P.bjt_nodes + 3 * q;
-            int B = nodes[0] - 1, C = nodes[1] - 1, E = nodes[2] - 1;
-            double out[kBjtWaves];
-            bjt_eval(bd[q], B >= 0 ? v[B * S + s] : 0., C >= 0 ? v[C * S + s] : 0., E >= 0 ? v[E * S + s] : 0.,
-                     B >= 0 ? vo[B * S + s] : 0., C >= 0 ? vo[C * S + s] : 0., E >= 0 ? vo[E * S + s] : 0., out);
-            double *o = bjt_out + ((size_t)b * P.nb + q) * kBjtWaves * S + s;
+                const int q = dev - P.nd - P.nc;
+                const int *nodes = P.bjt_nodes + 3 * q;
+                int B = nodes[0] - 1, C = nodes[1] - 1, E = nodes[2] - 1;
+                double out[kBjtWaves];
+                bjt_eval(bd[cl * P.nb + q], B >= 0 ? v[B * S + s] : 0., C >= 0 ? v[C * S + s] : 0.,
+                         E >= 0 ? v[E * S + s] : 0., B >= 0 ? vo[B * S + s] : 0., C >= 0 ? vo[C * S + s] : 0.,
+                         E >= 0 ? vo[E * S + s] : 0., out);
+                double *o = bjt_out + (b * P.nb + q) * kBjtWaves * S + s;
 #pragma unroll
-            for (int j = 0; j < kBjtWaves; ++j) o[(size_t)j * S] = out[j];
+                for (int j = 0; j < kBjtWaves; ++j) o[(size_t)j * S] = out[j];
+            }
         }
     }
 }
@@ -1012,12 +1022,18 @@ extern "C" int yhb_stage_device_eval(const yhb_plan *pl, const yhb_params *p, co
         set_error("missing array");
         return -1;
     }
-    size_t smem = d.nd * sizeof(DiodeDerived) + d.nb * sizeof(BjtDerived);
+    size_t smem = (size_t)kDevChunk * (d.nd * sizeof(DiodeDerived) + d.nb * sizeof(BjtDerived));
+    if (smem > 200 * 1024) { set_error("too many devices for the stage kernel"); return -1; }
     if (smem > 48 * 1024)
         YHB_CUDA(cudaFuncSetAttribute(k_stage_device_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stage_device_eval<<<p->batch, 256, smem, (cudaStream_t)stream>>>(d, p->batch, p->diode_par, p->bjt_par,
-                                                                       p->cubic_par, vt, vtprev, diode_out, bjt_out,
-                                                                       cubic_out);
+    int dev = 0, sms = 0;
+    YHB_CUDA(cudaGetDevice(&dev));
+    YHB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int chunks = (p->batch + kDevChunk - 1) / kDevChunk;
+    const int grid = std::min(chunks, 2 * sms);  // persistent: 2 resident CTAs per SM
+    k_stage_device_eval<<<grid, 256, smem, (cudaStream_t)stream>>>(d, p->batch, p->diode_par, p->bjt_par,
+                                                                   p->cubic_par, vt, vtprev, diode_out, bjt_out,
+                                                                   cubic_out);
     YHB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -116,8 +116,9 @@ __device__ inline void pn_eval(const PnJunction &j, double V, double &C, double 
     }
     if (V <= j.fcvj) {
         double base = 1. - V / j.Vj;
-        C = j.Cj * pow(base, -j.Mj);
-        Q = j.q1 * (1. - pow(base, j.one_m));
+        double pm = pow(base, -j.Mj);  // base^(1-Mj) = base * base^(-Mj): one pow instead of two (<= 1 ulp apart)
+        C = j.Cj * pm;
+        Q = j.q1 * (1. - base * pm);
     } else {
         C = j.c2 * (1. + j.Mj * (V - j.fcvj) / j.den);
         double r = V / j.Vj;
