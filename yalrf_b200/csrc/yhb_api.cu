@@ -948,7 +948,7 @@ __global__ void k_stage_ifft(PlanDev P, int batch, const double *V, double *vt) 
 // per sample).  Persistent CTAs walk chunks of kDevChunk circuits: the hoisted model constants of the chunk are
 // derived into shared memory by one thread per (circuit, device), then one thread per (circuit, device, sample)
 // evaluates; loads and stores are contiguous along the sample index.
-constexpr int kDevChunk = 16;
+constexpr int kDevChunk = 32;
 
 __global__ void __launch_bounds__(256, 2) k_stage_device_eval(PlanDev P, int batch, const double *diode_par,
                                                               const double *bjt_par, const double *cubic_par,

@@ -242,7 +242,9 @@ __device__ inline void bjt_eval(const BjtDerived &d, double Vb, double Vc, doubl
     }
 
     // transit time, BJT.py:556-558
-    double etf = exp_lim(Vbc / d.vtf144);
+    // Tf == 0 (no transit time): every use of etf below is multiplied by an exact zero, and exp_lim is finite and
+    // positive, so the exponential is skipped without changing any result (0 * finite = 0, NaN from rat survives)
+    double etf = (d.Tf != 0.) ? exp_lim(Vbc / d.vtf144) : 1.;
     double rat = If / (If + d.Itf);  // 0/0 = NaN at If = Itf = 0, as in the reference
     double Tff = d.Tf * (1. + d.Xtf * (rat * rat) * etf);
     double ipi = If + d.Itf;
