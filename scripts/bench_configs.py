@@ -1,0 +1,38 @@
+"""Timings of the other BASELINE.json configs on the GPU (not the bench line): python scripts/bench_configs.py"""
+import os, sys, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np, torch
+import circuits, yalrf_b200
+from yalrf_b200.Analyses import MultiToneHarmonicBalance
+
+def timeit(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(reps): out = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t) / reps, out
+
+res = {}
+# config 1: HB_Diode single + 4096-point I1.ac sweep
+y = yalrf_b200.YalRF('d'); h = circuits.hb_diode(y)
+hb = MultiToneHarmonicBalance('HB1', h['freq'], h['K'])
+dt, _ = timeit(lambda: hb.run(y)); res['cfg1_single_ms'] = dt * 1e3
+ac = np.linspace(0.5, 5, 4096)
+dt, r = timeit(lambda: hb.run_sweep(y, [(h['i1'], 'ac', ac)])); res['cfg1_sweep4096_solves_per_s'] = 4096 / dt; res['cfg1_converged'] = int(r.converged.sum())
+# config 3: two tones [3,3] and [8,8]
+for nh in ([3, 3], [8, 8]):
+    y = yalrf_b200.YalRF('d'); h = circuits.hb_diode_two_tones(y)
+    hb = MultiToneHarmonicBalance('HB1', h['freq'], nh)
+    dt, _ = timeit(lambda: hb.run(y), reps=2); res['cfg3_%dx%d_single_s' % tuple(nh)] = dt
+    res['cfg3_%dx%d_core' % tuple(nh)] = hb._plan.core()
+    B = 64
+    ac = np.linspace(0.1, 1.0, B)
+    dt, r = timeit(lambda: hb.run_sweep(y, [(h['i1'], 'ac', ac), (h['i2'], 'ac', ac)]), reps=1)
+    res['cfg3_%dx%d_sweep%d_solves_per_s' % (nh[0], nh[1], B)] = B / dt; res['cfg3_%dx%d_converged' % tuple(nh)] = int(r.converged.sum())
+# config 2: Peltz oscillator
+y = yalrf_b200.Netlist('o'); h = circuits.peltz(y)
+hb = MultiToneHarmonicBalance('HB1')
+t = time.perf_counter(); hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node']); res['cfg2_peltz_oscillator_s'] = time.perf_counter() - t
+res['cfg2_evals'] = len(hb.osc_evals); res['cfg2_fosc'] = hb.fosc
+print(json.dumps(res, indent=1))

@@ -755,7 +755,9 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
             }
             {
                 ProfScope ps(PK_LU, st);
-                k_solve_core<<<nsolve, kLuThreads, (d.Wc + 2) * sizeof(double), st>>>(d, ws, ea, cur ^ 1);
+                // large cores: the HBM-resident elimination is latency bound, more warps per circuit hide it
+                const int lu_threads = d.Wc >= 160 ? 1024 : kLuThreads;
+                k_solve_core<<<nsolve, lu_threads, (d.Wc + 2) * sizeof(double), st>>>(d, ws, ea, cur ^ 1);
             }
             YHB_CUDA(cudaGetLastError());
         }
