@@ -129,6 +129,7 @@ typedef struct {
     int32_t *level_iters;  /* [B][YHB_MAX_LEVELS]  'NR number of iterations' of each hb_loop call, 0-terminated */
     double *level_alpha;   /* [B][YHB_MAX_LEVELS]  'Alpha level' of each call (1.0 for the direct attempt) */
     double *err;           /* [B]  'HB total error' sum|F| of the last hb_loop call (:597)             */
+    double *Inl;           /* [B][W]  nonlinear current spectrum fft(it) + Omega fft(qt) (:584) at the returned V   */
 } yhb_result;
 
 const char *yhb_last_error(void);

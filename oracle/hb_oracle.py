@@ -1030,6 +1030,7 @@ class HBOracle:
             Il = Y @ V - Is
             Inl = self.fft(it) + self.apply_omega(self.fft(qt))
             F = Il + Inl
+            self.last_Inl = Inl          # kept for checks of the KCL-based oscillator objective (not in the reference)
             converged = self.hb_converged(Il, Inl)
             itercnt += 1
             self.total_newton += 1

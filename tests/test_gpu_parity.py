@@ -299,3 +299,60 @@ def test_vanderpol_oscillator(yb, golden):
     assert conv
     assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 1e-8
     assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 1e-8
+
+
+def test_oscillator_newton_batch(yb, golden):
+    """run_oscillator_batch: the scipy-free oscillator solve (2x2 Newton on (f, V), probe current from KCL).  Eight
+    start points land on one root to 1e-9; it lies within the resolution of the reference's Nelder-Mead answer
+    (see test_peltz_oscillator); the oracle, solving the same circuit with the probe fixed at that (f, V), finds
+    the probe carrying no current.  A capacitor sweep follows f ~ 1 / sqrt(L C)."""
+    from oracle import hb_oracle as ho
+    from yalrf_b200 import _osc
+    from yalrf_b200._flatten import ParamBlock, Topology
+    g = golden('peltz_osc')
+    y = yb.Netlist('Oscillator')
+    h = circuits.peltz(y)
+    hb = mthb('HB1')
+    f0 = np.linspace(70e3, 90e3, 8)
+    V0 = np.linspace(0.05, 0.8, 8)
+    r = hb.run_oscillator_batch(y, f0, h['K'], V0, h['node'])
+    assert r.converged.all(), (r.converged, r.yosc)
+    assert np.max(np.abs(r.fosc - r.fosc[0])) / r.fosc[0] < 1e-9
+    assert np.max(np.abs(r.Vosc - r.Vosc[0])) / r.Vosc[0] < 1e-9
+    assert np.max(r.yosc) < 1e-12
+    assert abs(r.fosc[0] - float(g['fosc'])) / float(g['fosc']) < 2e-5
+    assert abs(r.Vosc[0] - float(g['Vosc'])) / float(g['Vosc']) < 5e-5
+    # oracle check at the GPU answer: fixed probe, tight inner tolerance, KCL objective from the oracle's own V and Inl
+    yo = ho.FlatNetlist()
+    circuits.peltz(yo)
+    yo.add_iac('HB1.I.Oscprobe', 'HB1.nosc1', 'gnd', ac=float(r.Vosc[0]), freq=float(r.fosc[0]))
+    yo.add_gyrator('HB1.G.Oscprobe', 'HB1.nosc1', 'HB1.nosc2', 'gnd', 'gnd', 1)
+    yo.add_idealharmonicfilter('HB1IHF.Oscprobe', 'HB1.nosc2', 'nb', float(r.fosc[0]))
+    o = ho.HBOracle('HB1', float(r.fosc[0]), h['K'])
+    assert o.run(yo)[0]
+    for _ in range(3):                      # warm restarts: >= 3 more Newton iterations each (tolerances cannot be
+        assert o.run(yo, o.V)[0]            # tightened: the 1e9 S probe branch leaves 1e-7 A of rounding noise in F)
+    topo = Topology(r.netlist, 1, (h['K'],))
+    pb = ParamBlock(topo, float(r.fosc[0]), 1).finalize()
+    pz = [d for _, _, d in topo.lin if d.name == 'HB1IHF.Oscprobe'][0]
+    Y = _osc.kcl_yosc(topo, pb, pz, r.netlist.get_node_idx('nb'), o.V.reshape(1, -1), o.last_Inl.reshape(1, -1), 21)
+    assert abs(Y[0]) < 1e-10, abs(Y[0])   # vs |dYosc/df| = 1.3e-7 S/Hz: the root is located to < 1e-3 Hz
+    # parameter sweep: tank capacitance 5 ... 20 nF from one start point
+    c = np.linspace(5e-9, 20e-9, 6)
+    r2 = hb.run_oscillator_batch(y, 80e3, h['K'], 0.1, h['node'], sweeps=[(h['c1'], 'C', c)], maxiter=40)
+    assert r2.converged.all(), (r2.converged, r2.yosc)
+    f_lc = 1 / (2 * np.pi * np.sqrt(0.5e-3 * c))
+    assert np.all(np.abs(r2.fosc / f_lc - 1) < 0.01)
+    assert abs(r2.fosc[np.argmin(np.abs(c - 10e-9))] - r.fosc[0]) / r.fosc[0] < 0.35   # 10 nF is not on this grid
+
+
+def test_vanderpol_newton(yb, golden):
+    g = golden('vanderpol_osc')
+    y = yb.Netlist('vdp')
+    h = circuits.vanderpol(y)
+    hb = mthb('HB1')
+    r = hb.run_oscillator_batch(y, [h['f0'], 0.15], h['K'], [h['V0'], 1.0], h['node'])
+    assert r.converged.all(), (r.converged, r.yosc)
+    assert abs(r.fosc[0] - float(g['fosc'])) / float(g['fosc']) < 1e-7
+    assert abs(r.Vosc[0] - float(g['Vosc'])) / float(g['Vosc']) < 1e-7
+    assert abs(r.fosc[1] - r.fosc[0]) / r.fosc[0] < 1e-9

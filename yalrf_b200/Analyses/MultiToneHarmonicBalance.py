@@ -207,6 +207,16 @@ class MultiToneHarmonicBalance:
         print('Oscillation amplitude = {} V'.format(Vosc))
         return out
 
+    def run_oscillator_batch(self, netlist, f0, numharmonics, V0, node, sweeps=None, tol=1e-13, maxiter=30):
+        """Batched oscillator analysis without scipy.optimize: Newton on (fosc, Vosc) per oscillator, the probe
+        current taken from Kirchhoff's law at `node` (yalrf_b200/_osc.py).  f0 / V0: arrays of start points; sweeps
+        as in run_sweep.  Returns an object with fosc[B], Vosc[B], converged[B], yosc[B] (|Yosc| reached), Vf."""
+        from .. import _osc
+        res = _osc.solve(self, netlist, f0, numharmonics, V0, node, sweeps=sweeps, tol=tol, maxiter=maxiter)
+        self.netlist = res.netlist
+        self.last_osc = res
+        return res
+
     # ------------------------------------------------------------------ post-processing (:112-135)
     def print_v(self, node):
         n = self.get_node_idx(node)

@@ -136,10 +136,11 @@ def make_options(options):
     return o
 
 
-def run_host(plan, pb, options, V0=None):
+def run_host(plan, pb, options, V0=None, want_inl=False):
     """run() for a batch through yhb_run_host: host arrays in, host arrays out (H2D / D2H inside)."""
     pb.finalize()
     res = BatchResult(plan, pb.B)
+    res.Inl = np.zeros((pb.B, plan.W)) if want_inl else None
     r = L.Result()
     r.V = L.ptr(res.V)
     r.Vf = L.ptr(res.Vf)
@@ -149,6 +150,7 @@ def run_host(plan, pb, options, V0=None):
     r.level_iters = L.ptr(res.level_iters)
     r.level_alpha = L.ptr(res.level_alpha)
     r.err = L.ptr(res.err)
+    r.Inl = L.ptr(res.Inl)
     p = make_params(pb)
     o = make_options(options)
     v0 = None
@@ -199,6 +201,7 @@ class DeviceBatch:
                                                    self.lu_count.data_ptr())
         r.level_iters, r.level_alpha, r.err = (self.level_iters.data_ptr(), self.level_alpha.data_ptr(),
                                                self.err.data_ptr())
+        r.Inl = None
         self.result = r
 
     def solve(self, options, have_v0=False, stream=None):

@@ -49,7 +49,7 @@ class Options(C.Structure):
 class Result(C.Structure):
     _fields_ = [('V', C.c_void_p), ('Vf', C.c_void_p), ('converged', C.c_void_p), ('newton_iters', C.c_void_p),
                 ('lu_count', C.c_void_p), ('level_iters', C.c_void_p), ('level_alpha', C.c_void_p),
-                ('err', C.c_void_p)]
+                ('err', C.c_void_p), ('Inl', C.c_void_p)]
 
 
 _lib = None

@@ -605,6 +605,7 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.xstep = c.take<double>(L.fused ? 1 : B * ws.x_stride);
     ws.rhs = c.take<double>(L.fused ? 1 : (size_t)B * (d.Wc + 1));
     ws.pairwav = c.take<double>((size_t)B * std::max(d.npair_nl, 1) * 2 * S);
+    ws.Inl = nullptr;
     ws.list[0] = c.take<int>(B);
     ws.list[1] = c.take<int>(B);
     ws.count = c.take<int>(4);
@@ -819,6 +820,7 @@ static int solve_common(const yhb_plan *pl, const yhb_params *p, const yhb_optio
     if (have_v0 && !res->V) { set_error("have_v0 set but res->V is null"); return -1; }
     if (!have_v0 && !Vdc) { set_error("cold start needs Vdc"); return -1; }
     if (res->V) L.ws.V = res->V;
+    L.ws.Inl = res->Inl;
     if (Vdc) L.ws.dcV = const_cast<double *>(Vdc);
     L.ws.dc_valid = Vdc != nullptr;
     std::lock_guard<std::mutex> lk(const_cast<yhb_plan *>(pl)->mu);  // pinned counter buffer is per plan
@@ -864,6 +866,7 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
         dr.level_iters = cv.take<int32_t>(B * YHB_MAX_LEVELS);
         dr.level_alpha = cv.take<double>(B * YHB_MAX_LEVELS);
         dr.err = cv.take<double>(B);
+        dr.Inl = hr->Inl ? cv.take<double>(B * W) : nullptr;
         wsb = cv.take<char>(wsbytes);
     };
     const size_t wsbytes = yhb_workspace_bytes(pl, (int)B);
@@ -925,6 +928,7 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
     D2H(hr->level_iters, dr.level_iters, B * YHB_MAX_LEVELS);
     D2H(hr->level_alpha, dr.level_alpha, B * YHB_MAX_LEVELS);
     D2H(hr->err, dr.err, B);
+    D2H(hr->Inl, dr.Inl, B * W);
 #undef D2H
     YHB_CUDA(cudaStreamSynchronize(st));
     return 0;

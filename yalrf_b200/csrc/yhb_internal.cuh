@@ -124,6 +124,7 @@ struct Workspace {
     size_t scratch_stride;
     double *J;           // staged engine: core Jacobians [B][j_stride] (stage entry point: caller's full [B][W][W])
     size_t j_stride;
+    double *Inl;         // [B][W] optional output: nonlinear current spectrum of the last evaluation (or nullptr)
     double *pairwav;     // [B][npair_nl][2][S] pair conductance / capacitance waveforms (staged engine)
     double *xstep;       // [B][x_stride]  staged engine: Newton step vector + scratch of newton_pre / newton_post
     size_t x_stride;
