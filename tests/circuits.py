@@ -177,3 +177,77 @@ def ladder(y, stages=8, cje=0.0, seed=0, ac=1.0):
             d.options['Itf'] = 1e-3
         devs.append(d)
     return dict(devs=devs, freq=[1.1e6, 0.9e6])
+
+
+def current_mirror(y):
+    """tests/HB_CurrentMirror.py:10-24 (K = 5): two BJTs sharing one options dict?  No -- only Q1 is configured."""
+    y.add_iac('I1', 'n1', 'gnd', ac=3e-3, freq=1e6, phase=+90)
+    y.add_idc('I2', 'n1', 'gnd', dc=20e-3)
+    y.add_resistor('R1', 'n1', 'gnd', 200)
+    y.add_resistor('R2', 'n1', 'nc', 200)
+    y.add_idc('I3', 'nb', 'gnd', dc=10e-3)
+    q1 = y.add_bjt('Q1', 'nb', 'nc', 'gnd')
+    q2 = y.add_bjt('Q2', 'nb', 'nb', 'gnd')
+    q1.options['Is'] = 1e-15
+    q1.options['Bf'] = 100
+    q1.options['Vaf'] = 20
+    # Q2 keeps the defaults, whose Itf = 0 makes If / (If + Itf) = 0/0 when Vbe == 0 exactly; the DC point is not 0
+    return dict(q1=q1, q2=q2, freq=1e6, K=5)
+
+
+def fullwave_rectifier(y):
+    """tests/HB_FullWaveRectifier.py:22-48: four diodes, floating source (both source nodes non-ground)."""
+    y.add_iac('I1', 'vinp', 'vinn', ac=15e-3, phase=+90, freq=1e6)
+    y.add_idc('I2', 'vinp', 'vinn', dc=5e-3)
+    y.add_resistor('R1', 'vinp', 'vinn', 100)
+    y.add_resistor('R2', 'voutp', 'gnd', 100)
+    ds = [y.add_diode('D1', 'vinp', 'voutp'), y.add_diode('D2', 'vinn', 'voutp'),
+          y.add_diode('D3', 'gnd', 'vinp'), y.add_diode('D4', 'gnd', 'vinn')]
+    for d in ds:
+        d.options['Is'] = 1e-15
+        d.options['N'] = 1
+        d.options['Area'] = 1
+    return dict(d=ds, freq=1e6, K=10)
+
+
+def am_demod(y):
+    """tests/HB_AMDemod.py:10-26: two-tone envelope detector with a capacitor (run at [3,3] here)."""
+    y.add_iac('I1', 'nx', 'gnd', ac=5, freq=1e6)
+    y.add_gyrator('G1', 'nx', 'nz', 'gnd', 'gnd', 1)
+    y.add_iac('I2', 'ny', 'gnd', ac=0.5, freq=10e3)
+    y.add_gyrator('G2', 'ny', 'n1', 'nz', 'gnd', 1)
+    y.add_resistor('R1', 'n1', 'nd', 50)
+    y.add_resistor('R2', 'n2', 'gnd', 5e3)
+    y.add_capacitor('C1', 'n2', 'gnd', 2.2e-9)
+    d1 = y.add_diode('D1', 'nd', 'n2')
+    d1.options['Is'] = 1e-15
+    d1.options['N'] = 1
+    d1.options['Area'] = 1
+    return dict(d1=d1, freq=[1e6, 10e3])
+
+
+def colpitts_cb(y):
+    """tests/HBOsc_ColpittsCB.py:13-66: common-base Colpitts with the full charge model (Tf, Tr, Mje = 0.5 ...)."""
+    vcc, vee, re, l, c1, c2 = 3, -3, 2.2e3, 5e-6, 200e-12, 50e-12
+    y.add_idc('I1', 'nx1', 'gnd', dc=vcc)
+    y.add_gyrator('G1', 'nx1', 'nvcc', 'gnd', 'gnd', 1)
+    y.add_idc('I2', 'nx2', 'gnd', dc=vee)
+    y.add_gyrator('G2', 'nx2', 'nvee', 'gnd', 'gnd', 1)
+    y.add_resistor('Re', 'ne', 'nvee', re)
+    y.add_resistor('Rx', 'nvcc', 'nc', 8.73e3)
+    y.add_inductor('L1', 'nvcc', 'nc', l)
+    y.add_capacitor('C1', 'ne', 'nc', c1)
+    y.add_capacitor('C2', 'nvcc', 'ne', c2)
+    q1 = y.add_bjt('Q1', 'gnd', 'nc', 'ne')
+    q1.options.update({'Is': 10.2e-15, 'Bf': 301, 'Br': 4, 'Ne': 2, 'Nc': 2, 'Ise': 5.82e-12, 'Vaf': 121, 'Var': 24,
+                       'Ikf': 60.7e-3, 'Ikr': 0.15, 'Cje': 26.8e-12, 'Vje': 1.1, 'Mje': 0.5, 'Cjc': 8.67e-12,
+                       'Vjc': 0.3, 'Mjc': 0.3, 'Xcjc': 1, 'Cjs': 0, 'Vjs': 0.75, 'Mjs': 0, 'Fc': 0.5,
+                       'Tf': 427e-12, 'Tr': 50.3e-9})
+    return dict(q1=q1, f0=9e6, V0=1, K=20, node='nc')
+
+
+def add_probe(y, name, node, f, amp):
+    """The oscillator probe of run_oscillator (MultiToneHarmonicBalance.py:146-150) at a fixed (f, amplitude)."""
+    y.add_iac(name + '.I.Oscprobe', name + '.nosc1', 'gnd', ac=amp, freq=f)
+    y.add_gyrator(name + '.G.Oscprobe', name + '.nosc1', name + '.nosc2', 'gnd', 'gnd', 1)
+    return y.add_idealharmonicfilter(name + 'IHF.Oscprobe', name + '.nosc2', node, f)

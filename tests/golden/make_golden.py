@@ -98,6 +98,33 @@ def hb_W(hb, y):
     return (2 * K + 1) * (y.get_num_nodes() - 1)
 
 
+def extra_fixtures(Netlist, MTHB, save):
+    """Second batch of fixtures (more reference scripts): python tests/golden/make_golden.py --extra"""
+    import circuits
+    for tag, build, nh in (('current_mirror', circuits.current_mirror, None),
+                           ('fullwave_rectifier', circuits.fullwave_rectifier, None),
+                           ('am_demod_3x3', circuits.am_demod, [3, 3])):
+        y = Netlist(tag)
+        h = build(y)
+        hb = MTHB('HB1', h['freq'], nh if nh is not None else h['K'])
+        (conv, freqs, Vf, _, _), text = quiet_run(hb.run, y)
+        al, its, errs = parse_levels(text)
+        save(tag, converged=conv, freqs=freqs if conv else np.zeros(1), Vf=Vf if conv else np.zeros(1),
+             V=hb.V if conv else np.zeros(1), alphas=al, iters=its, errs=errs)
+    # Colpitts CB with the probe fixed at (9.5 MHz, 0.8 V): full BJT charge model (Tf, Tr, Cje, Cjc) in hb_loop
+    y = Netlist('colpitts')
+    h = circuits.colpitts_cb(y)
+    circuits.add_probe(y, 'HB1', 'nc', 9.5e6, 0.8)
+    hb = MTHB('HB1', 9.5e6, 8)
+    with Recorder(hb_W(hb, y)) as rec:
+        rec.on = True
+        (conv, freqs, Vf, _, _), text = quiet_run(hb.run, y)
+    al, its, errs = parse_levels(text)
+    save('colpitts_probe_fixed', converged=conv, freqs=freqs if conv else np.zeros(1), Vf=Vf if conv else np.zeros(1),
+         V=hb.V if conv else np.zeros(1), alphas=al, iters=its, errs=errs, J0=rec.J[0], F0=rec.F[0], J3=rec.J[3],
+         F3=rec.F[3])
+
+
 def main():
     import circuits
     Netlist, MTHB = import_reference()
@@ -107,6 +134,9 @@ def main():
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **arrs)
         print('wrote', path, {k: np.asarray(v).shape for k, v in arrs.items()})
+
+    if '--extra' in sys.argv:
+        return extra_fixtures(Netlist, MTHB, save)
 
     # ---- config 1: HB_Diode, cold start, plus tight-tolerance variant and two more drive levels
     for tag, ac, opts in (('hb_diode', 5.0, {}), ('hb_diode_tight', 5.0, {'reltol': 1e-9, 'abstol': 1e-12}),

@@ -356,3 +356,45 @@ def test_vanderpol_newton(yb, golden):
     assert abs(r.fosc[0] - float(g['fosc'])) / float(g['fosc']) < 1e-7
     assert abs(r.Vosc[0] - float(g['Vosc'])) / float(g['Vosc']) < 1e-7
     assert abs(r.fosc[1] - r.fosc[0]) / r.fosc[0] < 1e-9
+
+
+# ----------------------------------------------------------------------------- more reference scripts
+@pytest.mark.parametrize('tag,builder,nh', [('current_mirror', 'current_mirror', None),
+                                            ('fullwave_rectifier', 'fullwave_rectifier', None),
+                                            ('am_demod_3x3', 'am_demod', [3, 3])])
+def test_more_reference_scripts(yb, golden, tag, builder, nh):
+    """tests/HB_CurrentMirror.py (phase = +90 source, diode-connected BJT), HB_FullWaveRectifier.py (floating
+    source between two non-ground nodes, four diodes), HB_AMDemod.py at [3,3] (two tones 1 MHz / 10 kHz, capacitor)."""
+    g = golden(tag)
+    y = yb.YalRF(tag)
+    h = getattr(circuits, builder)(y)
+    hb = mthb('HB1', h['freq'], nh if nh is not None else h['K'])
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv == bool(g['converged'])
+    assert hb.last.levels() == g['iters'].tolist()
+    from test_oracle_golden import _check_extra
+    _check_extra(tag, hb.V, g['V'], hb.S)
+    if tag != 'fullwave_rectifier':
+        assert relmax(Vf, g['Vf']) < 1e-9
+    np.testing.assert_allclose(freqs, g['freqs'], rtol=1e-15)
+
+
+def test_colpitts_probe_fixed(yb, golden):
+    """Colpitts CB (tests/HBOsc_ColpittsCB.py netlist) with the probe fixed: BJT transit-time and depletion charges,
+    inductor, capacitors, two supply gyrators, K = 8."""
+    g = golden('colpitts_probe_fixed')
+    y = yb.Netlist('colpitts')
+    circuits.colpitts_cb(y)
+    circuits.add_probe(y, 'HB1', 'nc', 9.5e6, 0.8)
+    hb = mthb('HB1', 9.5e6, 8)
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv == bool(g['converged'])
+    assert hb.last.levels() == g['iters'].tolist()
+    from test_oracle_golden import colpitts_tolerance
+    tol = colpitts_tolerance()      # 20 x the reference algorithm's measured self-sensitivity to 1 ulp (about 1e-6)
+    V, G = hb.V.reshape(hb.N, hb.S), g['V'].reshape(hb.N, hb.S)
+    probe = y.get_node_idx('HB1.nosc1') - 1
+    for n in range(hb.N):
+        if n != probe:
+            assert np.max(np.abs(V[n] - G[n])) < tol * np.max(np.abs(G)), n
+    assert np.max(np.abs(V[probe] - G[probe])) < 1e9 * 16 * np.spacing(0.8) + tol * 1e-2   # probe current node
