@@ -97,19 +97,28 @@ def get_plan(netlist, freq, numharmonics, flags=0, match_tones=True):
     return plan, topo
 
 
+def _host_array(shape, dtype, pinned):
+    """zeroed host array; page-locked (through torch) when a GPU is present so that D2H copies run at full speed"""
+    if pinned:
+        import torch
+        tdt = {np.float64: torch.float64, np.int32: torch.int32, np.complex128: torch.complex128}[dtype]
+        return torch.zeros(shape, dtype=tdt, pin_memory=True).numpy()
+    return np.zeros(shape, dtype=dtype)
+
+
 class BatchResult:
     """Results of a batched solve (numpy, host)."""
 
-    def __init__(self, plan, B):
+    def __init__(self, plan, B, pinned=False):
         self.B = B
-        self.V = np.zeros((B, plan.W))
-        self.Vf = np.zeros((B, plan.N, plan.K + 1), dtype=np.complex128)
-        self.converged = np.zeros(B, dtype=np.int32)
-        self.newton_iters = np.zeros(B, dtype=np.int32)
-        self.lu_count = np.zeros(B, dtype=np.int32)
-        self.level_iters = np.zeros((B, L.MAX_LEVELS), dtype=np.int32)
-        self.level_alpha = np.zeros((B, L.MAX_LEVELS))
-        self.err = np.zeros(B)
+        self.V = _host_array((B, plan.W), np.float64, pinned)
+        self.Vf = _host_array((B, plan.N, plan.K + 1), np.complex128, pinned)
+        self.converged = _host_array((B,), np.int32, pinned)
+        self.newton_iters = _host_array((B,), np.int32, pinned)
+        self.lu_count = _host_array((B,), np.int32, pinned)
+        self.level_iters = _host_array((B, L.MAX_LEVELS), np.int32, pinned)
+        self.level_alpha = _host_array((B, L.MAX_LEVELS), np.float64, pinned)
+        self.err = _host_array((B,), np.float64, pinned)
 
     def levels(self, b=0):
         it = self.level_iters[b]
@@ -139,7 +148,7 @@ def make_options(options):
 def run_host(plan, pb, options, V0=None, want_inl=False):
     """run() for a batch through yhb_run_host: host arrays in, host arrays out (H2D / D2H inside)."""
     pb.finalize()
-    res = BatchResult(plan, pb.B)
+    res = BatchResult(plan, pb.B, pinned=pb.B >= 256)     # page-locked results for large batches
     res.Inl = np.zeros((pb.B, plan.W)) if want_inl else None
     r = L.Result()
     r.V = L.ptr(res.V)
