@@ -67,6 +67,7 @@ enum {
 #define YHB_FLAG_EXACT_JACOBIAN 2 /* re-zero dQdV every iteration (the reference accumulates it, :413/:438) */
 
 #define YHB_FLAG_NO_PEEL 4        /* factor the full W x W system (no structural peeling of ideal-source rows) */
+#define YHB_FLAG_NO_BAND 16       /* staged engine: dense core storage even when the core is block banded over nodes */
 #define YHB_FLAG_STAGED 8         /* force the staged engine (Jacobian in HBM) even when the circuit fits one SM */
 
 #define YHB_MAX_LEVELS 64 /* hb_loop calls recorded per solve: 1 direct attempt + <=50 continuation levels */
@@ -157,6 +158,9 @@ int yhb_plan_dims(const yhb_plan *plan, int32_t *N, int32_t *K, int32_t *S, int3
 /* size of the dense core left after peeling ideal-source rows / columns (Wc = Nc * S) and whether the fused
  * on-chip engine will be used for this plan */
 int yhb_plan_core(const yhb_plan *plan, int32_t *Nc, int32_t *Wc, int32_t *fused);
+/* half bandwidth kl = ku (in matrix elements) of the band storage the staged engine uses for a block-banded core
+ * (chains of nodes, BASELINE config 5), 0 = dense core */
+int yhb_plan_band(const yhb_plan *plan);
 /* real frequency of each bin of circuit tones (f1, f2), as self.freqs (:251, :271): host helper */
 int yhb_plan_freqs(const yhb_plan *plan, double f1, double f2, double *freqs /* [K+1] */);
 

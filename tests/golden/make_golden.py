@@ -137,6 +137,16 @@ def main():
 
     if '--extra' in sys.argv:
         return extra_fixtures(Netlist, MTHB, save)
+    if '--ladder' in sys.argv:   # config 5 reductions: minutes of reference time
+        for tag, stages, nh in (('ladder32_4x4', 32, [4, 4]), ('ladder64_2x2', 64, [2, 2])):
+            y = Netlist('ladder')
+            h = circuits.ladder(y, stages=stages, cje=0.0)
+            hb = MTHB('HB1', h['freq'], nh)
+            (conv, freqs, Vf, _, _), text = quiet_run(hb.run, y)
+            al, its, errs = parse_levels(text)
+            save(tag, converged=conv, freqs=freqs if conv else np.zeros(1), Vf=Vf if conv else np.zeros(1),
+                 V=hb.V if conv else np.zeros(1), alphas=al, iters=its, errs=errs)
+        return
 
     # ---- config 1: HB_Diode, cold start, plus tight-tolerance variant and two more drive levels
     for tag, ac, opts in (('hb_diode', 5.0, {}), ('hb_diode_tight', 5.0, {'reltol': 1e-9, 'abstol': 1e-12}),

@@ -398,3 +398,48 @@ def test_colpitts_probe_fixed(yb, golden):
         if n != probe:
             assert np.max(np.abs(V[n] - G[n])) < tol * np.max(np.abs(G)), n
     assert np.max(np.abs(V[probe] - G[probe])) < 1e9 * 16 * np.spacing(0.8) + tol * 1e-2   # probe current node
+
+
+# ----------------------------------------------------------------------------- config 5 reductions: block-banded cores
+@pytest.mark.parametrize('stages,nh', [(16, [2, 2]), (24, [3, 3])])
+def test_ladder_banded_vs_oracle(yb, stages, nh):
+    """Diode / diode-connected-BJT ladder at oracle-checkable sizes: the core is block
+    tridiagonal over the ladder nodes, the staged engine stores and eliminates it in band form."""
+    from oracle import hb_oracle as ho
+    y = yb.Netlist('ladder')
+    h = circuits.ladder(y, stages=stages, cje=0.0)
+    hb = mthb('HB1', h['freq'], nh)
+    conv, freqs, Vf, _, _ = hb.run(y)
+    Nc, Wc, fused = hb._plan.core()
+    assert not fused and hb._plan.band() > 0 and 3 * hb._plan.band() + 1 < Wc
+    yo = ho.FlatNetlist()
+    circuits.ladder(yo, stages=stages, cje=0.0)
+    o = ho.HBOracle('HB1', h['freq'], nh)
+    conv_o = o.run(yo)[0]
+    assert conv == conv_o
+    assert hb.last.levels() == [l[1] for l in o.level_log]
+    assert relmax(hb.V, o.V) < 1e-9
+    # dense storage of the same core gives the same answer
+    hb2 = mthb('HB1', h['freq'], nh)
+    hb2.band = False
+    conv2, _, _, _, _ = hb2.run(y)
+    assert hb2._plan.band() == 0 and conv2 == conv
+    assert relmax(hb2.V, hb.V) < 1e-11
+
+
+@pytest.mark.parametrize('tag,stages,nh', [('ladder32_4x4', 32, [4, 4]), ('ladder64_2x2', 64, [2, 2])])
+def test_ladder_golden(yb, golden, tag, stages, nh):
+    """SURVEY 8d's oracle-checkable reductions of config 5, against the unmodified reference."""
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, tag + '.npz')):
+        pytest.skip('fixture not generated')
+    g = golden(tag)
+    y = yb.Netlist('ladder')
+    h = circuits.ladder(y, stages=stages, cje=0.0)
+    hb = mthb('HB1', h['freq'], nh)
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv == bool(g['converged'])
+    assert hb.last.levels() == g['iters'].tolist()
+    if conv:
+        assert relmax(hb.V, g['V']) < 1e-9

@@ -31,13 +31,15 @@ class MultiToneHarmonicBalance:
         self.verbose = False          # print the reference's per-level log lines (:354, :358, :383-384, :597-598)
         self.engine = 'auto'          # 'auto': fused on-chip engine when the circuit fits one SM; 'staged': HBM Jacobian
         self.peel = True              # eliminate ideal-source rows symbolically before the dense factorisation
+        self.band = True              # staged engine: band storage for block-banded cores (chains of nodes)
         self.distributed = False      # run_batch / run_sweep: shard the circuits over torch.distributed ranks, gather
         self.last = None              # BatchResult of the last call
 
     # ------------------------------------------------------------------ helpers
     def _flags(self):
         return ((L.FLAG_PNP_EXTENSION if self.pnp_extension else 0) | (L.FLAG_EXACT_JACOBIAN if self.exact_jacobian else 0) |
-                (0 if self.peel else L.FLAG_NO_PEEL) | (L.FLAG_STAGED if self.engine == 'staged' else 0))
+                (0 if self.peel else L.FLAG_NO_PEEL) | (L.FLAG_STAGED if self.engine == 'staged' else 0) |
+                (0 if self.band else L.FLAG_NO_BAND))
 
     def _setup(self, netlist):
         self.netlist = netlist.copy()

@@ -64,6 +64,10 @@ class Plan:
         L.check(L.lib().yhb_plan_core(self.handle, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, bool(c.value)
 
+    def band(self):
+        """half bandwidth (matrix elements) of the staged engine's band storage, 0 = dense core"""
+        return int(L.lib().yhb_plan_band(self.handle))
+
     def freqs(self, f1, f2=0.0):
         out = np.zeros(self.K + 1)
         L.check(L.lib().yhb_plan_freqs(self.handle, float(f1), float(f2), out.ctypes.data_as(C.POINTER(C.c_double))))

@@ -413,6 +413,18 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     for (int n = 0; n < N; ++n) if (act_col[n]) { core_col_of[n] = (int)core_cols.size(); core_cols.push_back(n); }
     d.Nc = (int)core_rows.size();
     d.Wc = d.Nc * S;
+    // block bandwidth of the core in its row / column orderings (chains of nodes give block-tridiagonal cores)
+    {
+        int bwn = 0;
+        for (int r = 0; r < d.Nc; ++r)
+            for (int p : row_cols[core_rows[r]]) {
+                int cpos = core_col_of[pairs[p].second];
+                if (cpos >= 0) bwn = std::max(bwn, std::abs(cpos - r));
+            }
+        const int kl = (bwn + 1) * S - 1;
+        // worth band storage when the band (3 kl + 1 per row) is well below the dense row
+        d.band = (!(desc->flags & YHB_FLAG_NO_BAND) && d.Nc > 0 && (long)3 * kl + 1 < (long)d.Wc / 2) ? kl : 0;
+    }
     d.nA = (int)a_row.size();
     d.nB = (int)b_row.size();
     std::vector<int> a_ptr(1, 0), a_pair, a_m, b_ptr(1, 0), b_pair, b_m, r_ptr(1, 0), r_pair, r_m;
@@ -532,6 +544,8 @@ extern "C" int yhb_plan_dims(const yhb_plan *pl, int32_t *N, int32_t *K, int32_t
     return 0;
 }
 
+extern "C" int yhb_plan_band(const yhb_plan *pl) { return pl ? pl->d.band : -1; }
+
 extern "C" int yhb_plan_core(const yhb_plan *pl, int32_t *Nc, int32_t *Wc, int32_t *fused) {
     if (!pl) { set_error("null plan"); return -1; }
     if (Nc) *Nc = pl->d.Nc;
@@ -599,7 +613,7 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.scratch = c.take<double>(L.eval_smem ? 1 : (size_t)B * esd);
     L.fc = fused_choice(d);
     L.fused = L.fc.ok;
-    ws.j_stride = L.fused ? 0 : (size_t)d.Wc * d.Wc;
+    ws.j_stride = L.fused ? 0 : (d.band > 0 ? (size_t)d.Wc * band_ld(d.band) : (size_t)d.Wc * d.Wc);
     ws.J = c.take<double>(L.fused ? 1 : (size_t)B * ws.j_stride);
     ws.x_stride = W + newton_scratch_doubles(d);
     ws.xstep = c.take<double>(L.fused ? 1 : B * ws.x_stride);
@@ -758,7 +772,8 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
                 ProfScope ps(PK_LU, st);
                 // large cores: the HBM-resident elimination is latency bound, more warps per circuit hide it
                 const int lu_threads = d.Wc >= 160 ? 1024 : kLuThreads;
-                k_solve_core<<<nsolve, lu_threads, (d.Wc + 2) * sizeof(double), st>>>(d, ws, ea, cur ^ 1);
+                const size_t rowbuf = d.band > 0 ? std::min<size_t>(d.Wc, 2 * (size_t)d.band + 1) + 3 : (size_t)d.Wc + 2;
+                k_solve_core<<<nsolve, lu_threads, rowbuf * sizeof(double), st>>>(d, ws, ea, cur ^ 1);
             }
             YHB_CUDA(cudaGetLastError());
         }

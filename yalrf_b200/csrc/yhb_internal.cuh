@@ -66,6 +66,7 @@ struct PlanDev {
     // B-steps (column singletons): the same formula, evaluated in REVERSE order after the core solve.
     // Core: J[core_rows, core_cols] y = F[core_rows] - sum_{A-known m} J[row, m] dV[m].
     int Nc, Wc, nA, nB;
+    int band;  // > 0: the core is block banded over nodes; kl = ku = band (in matrix elements), band storage
     const int *core_rows, *core_cols;  // [Nc] node indices
     const int *core_col_of;            // [N] -> position among core_cols or -1
     const int *a_row, *a_col, *a_sgn;  // [nA]
