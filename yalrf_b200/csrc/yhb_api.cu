@@ -34,27 +34,29 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 
 struct FusedChoice {
     bool ok;
-    int T;        // register tile (0 = core system in shared memory)
+    int NT;       // register tiles per dimension (0 = core system in shared memory)
     size_t smem;  // dynamic shared memory bytes
 };
 
 constexpr size_t kMaxEvalSmem = 200 * 1024;
+
+// instantiated register-tile counts of the fused engine (a core of Wc unknowns needs Wc + 1 <= 8 NT)
+#define YHB_FOR_NT(X) X(3) X(6) X(8) X(11) X(16)
 
 // which fused-engine variant runs this plan (if any)
 static FusedChoice fused_choice(const PlanDev &d) {
     constexpr size_t lim = 227 * 1024 - 2048;  // dynamic part: the 227 KB per-CTA limit includes the static __shared__
     FusedChoice f{false, 0, 0};
     if (d.flags & YHB_FLAG_STAGED) return f;
-    const int T = std::max(1, (d.Wc + 1 + 31) / 32);  // register tile: T rows x 4 T columns per thread
-    size_t b = 0;
-    switch (T) {
-#define YHB_CASE(t) case t: b = fused_smem_doubles<t>(d) * sizeof(double); break;
-        YHB_CASE(1) YHB_CASE(2) YHB_CASE(3) YHB_CASE(4)
-#undef YHB_CASE
-        default: b = 0;
+    const int need = std::max(1, (d.Wc + 1 + 7) / 8);
+#define YHB_CASE(t)                                                            \
+    if (need <= t) {                                                           \
+        size_t b = fused_smem_doubles<t>(d) * sizeof(double);                  \
+        if (b <= lim) return FusedChoice{true, t, b};                          \
     }
-    if (b > 0 && b <= lim) return FusedChoice{true, T, b};
-    b = fused_smem_doubles<0>(d) * sizeof(double);
+    YHB_FOR_NT(YHB_CASE)
+#undef YHB_CASE
+    size_t b = fused_smem_doubles<0>(d) * sizeof(double);
     if (b <= lim) return FusedChoice{true, 0, b};
     return f;
 }
@@ -733,13 +735,13 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
     case t: {                                                                                                 \
         YHB_CUDA(cudaFuncSetAttribute(k_fused<t>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));        \
         int per_sm = 0;                                                                                       \
-        YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<t>, kFusedThreads, fsmem));   \
+        YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<t>, fused_threads(t), fsmem)); \
         const int grid = std::min(B, std::max(1, per_sm) * sms);                                              \
         ProfScope ps(PK_FUSED, st);                                                                           \
-        k_fused<t><<<grid, kFusedThreads, fsmem, st>>>(d, ws, ea);                                            \
+        k_fused<t><<<grid, fused_threads(t), fsmem, st>>>(d, ws, ea);                                         \
     } break;
-        switch (L.fc.T) {
-            YHB_LAUNCH_FUSED(0) YHB_LAUNCH_FUSED(1) YHB_LAUNCH_FUSED(2) YHB_LAUNCH_FUSED(3) YHB_LAUNCH_FUSED(4)
+        switch (L.fc.NT) {
+            YHB_LAUNCH_FUSED(0) YHB_FOR_NT(YHB_LAUNCH_FUSED)
             default: set_error("no fused kernel for this core size"); return -4;
         }
 #undef YHB_LAUNCH_FUSED
@@ -1091,16 +1093,17 @@ extern "C" int yhb_stage_assemble(const yhb_plan *pl, const yhb_params *p, void 
 extern "C" int yhb_stage_gj(int32_t batch, int32_t n, const double *A, const double *F, double *x, void *stream) {
     if (batch < 1 || n < 1 || n > 127 || !A || !F || !x) { set_error("bad argument (1 <= n <= 127)"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int T = (n + 1 + 31) / 32;
-    switch (T) {
+    const int need = (n + 1 + 7) / 8;
+    bool done = false;
 #define YHB_CASE(t)                                                                                         \
-    case t: {                                                                                               \
-        size_t smem = (sizeof(GjBufs<t>) + 7) / 8 * 8 + (size_t)(n + 1) * sizeof(double);                   \
-        k_gj_stage<t><<<batch, 256, smem, st>>>(batch, n, A, F, x);                                         \
-    } break;
-        YHB_CASE(1) YHB_CASE(2) YHB_CASE(3) YHB_CASE(4)
-#undef YHB_CASE
+    if (!done && need <= t) {                                                                               \
+        size_t smem = (GjBufs<t>::kMatrixDoubles + (sizeof(GjBufs<t>) + 7) / 8 + (size_t)(n + 1)) * sizeof(double); \
+        YHB_CUDA(cudaFuncSetAttribute(k_gj_stage<t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_gj_stage<t><<<batch, fused_threads(t), smem, st>>>(batch, n, A, F, x);                            \
+        done = true;                                                                                        \
     }
+    YHB_FOR_NT(YHB_CASE)
+#undef YHB_CASE
     YHB_CUDA(cudaGetLastError());
     return 0;
 }
