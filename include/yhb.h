@@ -151,6 +151,13 @@ int yhb_profile_read(int64_t *launches /* [YHB_PROF_KINDS] */, double *ms /* [YH
  * in TFLOP/s: the roofline denominator of the LU stage (MEASURED_PEAKS.json has no fp64 figure). */
 int yhb_fp64_peak(double *tflops, void *stream);
 
+/* Debug builds only (csrc/build.sh -DYHB_TIMING): clock64() cycles of the fused engine's phases summed over all
+ * CTAs since the last reset.  Slots: 0 evaluation, 1 peeled rows / right-hand side, 2 core assembly, 3 core solve,
+ * 4 back-substitution of the peeled rows + update, 5 ladder bookkeeping; 8 panel factorisation (owner warp),
+ * 10-12 barrier wait (owner / next owner / other warps), 13-14 trailing update (next owner / other warps).
+ * The production build returns -1. */
+int yhb_debug_timing(unsigned long long *out64 /* [64] */, int32_t reset);
+
 /* plan = the setup part of run() (:234-302): grid sizes, DFT/IDFT tables, stamp tables */
 int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out);
 void yhb_plan_destroy(yhb_plan *plan);

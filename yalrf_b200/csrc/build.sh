@@ -3,7 +3,7 @@
 # reference's separately-rounded scalar arithmetic; the hot loops use explicit fma().
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../libyhb.so"
+OUT="${YHB_OUT:-$HERE/../libyhb.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a \
     -Xcompiler -fPIC,-O2,-Wall -shared -o "$OUT" "$HERE/yhb_api.cu" "$@"

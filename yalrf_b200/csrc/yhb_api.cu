@@ -34,30 +34,33 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 
 struct FusedChoice {
     bool ok;
-    int NT;       // register tiles per dimension (0 = core system in shared memory)
+    int NT;       // 8 x 8 tiles per dimension of the core system (0 = scalar elimination in shared memory)
     size_t smem;  // dynamic shared memory bytes
+    int hot;      // plan tables staged in shared memory
 };
 
 constexpr size_t kMaxEvalSmem = 200 * 1024;
 
-// instantiated register-tile counts of the fused engine (a core of Wc unknowns needs Wc + 1 <= 8 NT)
+// instantiated tile counts of the fused engine (a core of Wc unknowns needs Wc + 1 <= 8 NT)
 #define YHB_FOR_NT(X) X(3) X(6) X(8) X(11) X(16)
 
 // which fused-engine variant runs this plan (if any)
 static FusedChoice fused_choice(const PlanDev &d) {
     constexpr size_t lim = 227 * 1024 - 2048;  // dynamic part: the 227 KB per-CTA limit includes the static __shared__
-    FusedChoice f{false, 0, 0};
+    FusedChoice f{false, 0, 0, 0};
     if (d.flags & YHB_FLAG_STAGED) return f;
     const int need = std::max(1, (d.Wc + 1 + 7) / 8);
-#define YHB_CASE(t)                                                            \
-    if (need <= t) {                                                           \
-        size_t b = fused_smem_doubles<t>(d) * sizeof(double);                  \
-        if (b <= lim) return FusedChoice{true, t, b};                          \
+    for (int hot = 1; hot >= 0; --hot) {
+#define YHB_CASE(t)                                                                 \
+    if (need <= t) {                                                                \
+        size_t b = fused_smem_doubles<t>(d, hot != 0) * sizeof(double);             \
+        if (b <= lim) return FusedChoice{true, t, b, hot};                          \
     }
-    YHB_FOR_NT(YHB_CASE)
+        YHB_FOR_NT(YHB_CASE)
 #undef YHB_CASE
-    size_t b = fused_smem_doubles<0>(d) * sizeof(double);
-    if (b <= lim) return FusedChoice{true, 0, b};
+        size_t b = fused_smem_doubles<0>(d, hot != 0) * sizeof(double);
+        if (b <= lim) return FusedChoice{true, 0, b, hot};
+    }
     return f;
 }
 
@@ -458,9 +461,6 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
             if (pair_of[(size_t)n * N + m] >= 0) row_pairs.push_back(pair_of[(size_t)n * N + m]);
         row_ptr[n + 1] = (int)row_pairs.size();
     }
-    std::vector<int> ptr;
-    std::vector<Term> terms;
-
     // DFT tables: caller's (reference-identical numpy tables) or analytic (:294-302)
     std::vector<double> idft((size_t)S * S), dft((size_t)S * S);
     if (desc->idft && desc->dft) {
@@ -481,15 +481,20 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
         }
     }
 
+    // All plan tables live in ONE device blob; the tables the Newton loop reads ("hot": transforms, stamp lists,
+    // peeling lists) come first so that the fused engine can stage that prefix in shared memory (k_fused).
     bool ok = true;
-#define UP(field, vec) do { d.field = upload(pl, vec); ok = ok && d.field; } while (0)
+    std::vector<char> blob;
+    std::vector<std::pair<const void **, size_t>> fix;
+    auto stage = [&](const void **field, const void *data, size_t bytes) {
+        size_t off = align_up(blob.size(), 16);
+        blob.resize(off + std::max<size_t>(bytes, 16));
+        if (bytes) memcpy(blob.data() + off, data, bytes);
+        fix.push_back({field, off});
+    };
+#define UP(field, vec) stage(reinterpret_cast<const void **>(&d.field), (vec).data(), (vec).size() * sizeof((vec)[0]))
     UP(idft, idft);
     UP(dft, dft);
-    UP(bin_k1, pl->bin_k1);
-    UP(bin_k2, pl->bin_k2);
-    UP(lin_kind, pl->lin_kind);
-    UP(src_kind, pl->src_kind);
-    UP(src_nodes, pl->src_nodes);
     UP(diode_nodes, pl->diode_nodes);
     UP(bjt_nodes, pl->bjt_nodes);
     UP(cubic_nodes, pl->cubic_nodes);
@@ -499,17 +504,36 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     UP(pair_of, pair_of);
     UP(row_ptr, row_ptr);
     UP(row_pairs, row_pairs);
-    plin.flatten(d.npair, ptr, terms); UP(plin_ptr, ptr); UP(plin, terms);
-    pg.flatten(d.npair_nl, ptr, terms); UP(pg_ptr, ptr); UP(pg, terms);
-    pc.flatten(d.npair_nl, ptr, terms); UP(pc_ptr, ptr); UP(pc, terms);
-    ni.flatten(N, ptr, terms); UP(ni_ptr, ptr); UP(ni, terms);
-    nq.flatten(N, ptr, terms); UP(nq_ptr, ptr); UP(nq, terms);
-    ns.flatten(N, ptr, terms); UP(ns_ptr, ptr); UP(ns, terms);
+    std::vector<int> ptr_pg, ptr_pc, ptr_ni, ptr_nq, ptr_ns, ptr_plin;
+    std::vector<Term> t_pg, t_pc, t_ni, t_nq, t_ns, t_plin;
+    pg.flatten(d.npair_nl, ptr_pg, t_pg); UP(pg_ptr, ptr_pg); UP(pg, t_pg);
+    pc.flatten(d.npair_nl, ptr_pc, t_pc); UP(pc_ptr, ptr_pc); UP(pc, t_pc);
+    ni.flatten(N, ptr_ni, t_ni); UP(ni_ptr, ptr_ni); UP(ni, t_ni);
+    nq.flatten(N, ptr_nq, t_nq); UP(nq_ptr, ptr_nq); UP(nq, t_nq);
     UP(core_rows, core_rows); UP(core_cols, core_cols); UP(core_col_of, core_col_of);
     UP(a_row, a_row); UP(a_col, a_col); UP(a_sgn, a_sgn); UP(a_ptr, a_ptr); UP(a_pair, a_pair); UP(a_m, a_m);
     UP(b_row, b_row); UP(b_col, b_col); UP(b_sgn, b_sgn); UP(b_ptr, b_ptr); UP(b_pair, b_pair); UP(b_m, b_m);
     UP(r_ptr, r_ptr); UP(r_pair, r_pair); UP(r_m, r_m);
+    d.blob_hot_bytes = (int)align_up(blob.size(), 16);
+    // k_prepare / k_dc only
+    UP(bin_k1, pl->bin_k1);
+    UP(bin_k2, pl->bin_k2);
+    UP(lin_kind, pl->lin_kind);
+    UP(src_kind, pl->src_kind);
+    UP(src_nodes, pl->src_nodes);
+    plin.flatten(d.npair, ptr_plin, t_plin); UP(plin_ptr, ptr_plin); UP(plin, t_plin);
+    ns.flatten(N, ptr_ns, t_ns); UP(ns_ptr, ptr_ns); UP(ns, t_ns);
 #undef UP
+    {
+        void *dblob = nullptr;
+        ok = cudaMalloc(&dblob, align_up(blob.size(), 256)) == cudaSuccess;
+        if (ok) {
+            pl->allocs.push_back(dblob);
+            ok = cudaMemcpy(dblob, blob.data(), blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+            d.blob = reinterpret_cast<const char *>(dblob);
+            for (auto &f : fix) *f.first = d.blob + f.second;
+        }
+    }
     pl->lin_nodes_dev = upload(pl, pl->lin_nodes);
     pl->nl_kind_dev = upload(pl, pl->nl_kind);
     pl->nl_index_dev = upload(pl, pl->nl_index);
@@ -604,7 +628,7 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.vtprev = c.take<double>(B * W);
     ws.F = c.take<double>(B * W);
     ws.cacc = c.take<double>((size_t)B * std::max(d.nb, 1) * 4 * S);
-    ws.spec = c.take<double>((size_t)B * std::max(d.npair_nl, 1) * 4 * S);
+    ws.spec = c.take<double>((size_t)B * std::max(d.npair_nl, 1) * 2 * S);
     ws.ylin = c.take<double>((size_t)B * d.npair * K1 * 2);
     ws.omega = c.take<double>(B * K1);
     ws.negbin = c.take<int>(B * K1);
@@ -738,7 +762,7 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
         YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<t>, fused_threads(t), fsmem)); \
         const int grid = std::min(B, std::max(1, per_sm) * sms);                                              \
         ProfScope ps(PK_FUSED, st);                                                                           \
-        k_fused<t><<<grid, fused_threads(t), fsmem, st>>>(d, ws, ea);                                         \
+        k_fused<t><<<grid, fused_threads(t), fsmem, st>>>(d, ws, ea, L.fc.hot);                                      \
     } break;
         switch (L.fc.NT) {
             YHB_LAUNCH_FUSED(0) YHB_FOR_NT(YHB_LAUNCH_FUSED)
@@ -1158,4 +1182,20 @@ extern "C" int yhb_fp64_peak(double *tflops, void *stream) {
     YHB_CUDA(cudaGetLastError());
     *tflops = 2.0 * 8 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
     return 0;
+}
+
+// ---- phase timing of the fused engine (debug builds only: -DYHB_TIMING) -------------------------------
+extern "C" int yhb_debug_timing(unsigned long long *out64, int32_t reset) {
+#ifdef YHB_TIMING
+    if (out64) YHB_CUDA(cudaMemcpyFromSymbol(out64, yhb::g_timing, sizeof(unsigned long long) * 64));
+    if (reset) {
+        unsigned long long z[64] = {0};
+        YHB_CUDA(cudaMemcpyToSymbol(yhb::g_timing, z, sizeof(z)));
+    }
+    return 0;
+#else
+    (void)out64; (void)reset;
+    set_error("libyhb was built without -DYHB_TIMING");
+    return -1;
+#endif
 }

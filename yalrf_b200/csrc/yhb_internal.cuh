@@ -74,7 +74,17 @@ struct PlanDev {
     const int *b_row, *b_col, *b_sgn;  // [nB]
     const int *b_ptr, *b_pair, *b_m;
     const int *r_ptr, *r_pair, *r_m;   // per core row: entries in A-known columns, CSR [Nc+1]
+    // every table above points into one device blob; its first blob_hot_bytes hold what the Newton loop reads
+    const char *blob;
+    int blob_hot_bytes;
 };
+
+// pointer fields of PlanDev that lie in the hot prefix of the blob (re-based onto a shared-memory copy by k_fused)
+#define YHB_HOT_TABLES(X)                                                                                      \
+    X(idft) X(dft) X(diode_nodes) X(bjt_nodes) X(cubic_nodes) X(dev_wave_base) X(pair_n) X(pair_m) X(pair_of) \
+    X(row_ptr) X(row_pairs) X(pg_ptr) X(pg) X(pc_ptr) X(pc) X(ni_ptr) X(ni) X(nq_ptr) X(nq) X(core_rows)      \
+    X(core_cols) X(core_col_of) X(a_row) X(a_col) X(a_sgn) X(a_ptr) X(a_pair) X(a_m) X(b_row) X(b_col)        \
+    X(b_sgn) X(b_ptr) X(b_pair) X(b_m) X(r_ptr) X(r_pair) X(r_m)
 
 struct Plan {
     PlanDev d;                  // device view
@@ -114,7 +124,7 @@ struct Workspace {
     double *vtprev;      // [B][W]   previous iterate's time samples (limiter reference)
     double *F;           // [B][W]
     double *cacc;        // [B][nb][4][S] accumulated capacitance waveforms (never-reset dQdV)
-    double *spec;        // [B][npair_nl][4][S]  reG, imG, reC, imC for m = 0..2K
+    double *spec;        // [B][npair_nl][2][S]  DFT of the pair conductance / capacitance waveforms
     double *ylin;        // [B][npair][K+1][2]
     double *omega;       // [B][K+1]
     int *negbin;         // [B][K+1] real frequency of the bin is negative (two-tone, :725)
