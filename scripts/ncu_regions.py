@@ -13,7 +13,7 @@ marks = [('eval_pass', line_of('__device__ inline int eval_pass')), ('advance/ap
          ('assemble/ge', line_of('constexpr int kAsmRows')), ('newton pre/post', line_of('__device__ __forceinline__ double lin_dot')),
          ('staged', line_of('k_assemble_core(PlanDev')), ('gj factor', line_of('__device__ __forceinline__ void gj_factor_panel')),
          ('gj loop', line_of('__device__ __forceinline__ void gj_solve_mma')), ('gj stage', line_of('k_gj_stage(int batch')),
-         ('fused body', line_of('k_fused(PlanDev')), ('end', len(src) + 1)]
+         ('fused body', line_of('k_fused(const __grid_constant__')), ('end', len(src) + 1)]
 hdr = None; cur = None; out = []
 for r in rows:
     if len(r) == 2 and r[0] == 'File Path': cur = r[1].split('/')[-1]
