@@ -69,6 +69,11 @@ enum {
 #define YHB_FLAG_NO_PEEL 4        /* factor the full W x W system (no structural peeling of ideal-source rows) */
 #define YHB_FLAG_NO_BAND 16       /* staged engine: dense core storage even when the core is block banded over nodes */
 #define YHB_FLAG_STAGED 8         /* force the staged engine (Jacobian in HBM) even when the circuit fits one SM */
+#define YHB_FLAG_BLOCK_THOMAS 32  /* staged engine: solve a block-TRIdiagonal core block by block (S x S node blocks,
+                                     pivoting inside the diagonal blocks) even when it is small; chosen automatically
+                                     for large blocks (config 5: ladders at many harmonics), where the one-CTA banded
+                                     elimination is out of reach */
+#define YHB_FLAG_NO_BLOCK_THOMAS 64
 
 #define YHB_MAX_LEVELS 64 /* hb_loop calls recorded per solve: 1 direct attempt + <=50 continuation levels */
 
@@ -168,6 +173,8 @@ int yhb_plan_core(const yhb_plan *plan, int32_t *Nc, int32_t *Wc, int32_t *fused
 /* half bandwidth kl = ku (in matrix elements) of the band storage the staged engine uses for a block-banded core
  * (chains of nodes, BASELINE config 5), 0 = dense core */
 int yhb_plan_band(const yhb_plan *plan);
+/* which engine yhb_solve runs for this plan: 0 fused (on chip), 1 staged dense, 2 staged banded, 3 staged block-Thomas */
+int yhb_plan_engine(const yhb_plan *plan);
 /* real frequency of each bin of circuit tones (f1, f2), as self.freqs (:251, :271): host helper */
 int yhb_plan_freqs(const yhb_plan *plan, double f1, double f2, double *freqs /* [K+1] */);
 

@@ -427,8 +427,29 @@ def test_ladder_banded_vs_oracle(yb, stages, nh):
     assert relmax(hb2.V, hb.V) < 1e-11
 
 
-@pytest.mark.parametrize('tag,stages,nh', [('ladder32_4x4', 32, [4, 4]), ('ladder64_2x2', 64, [2, 2])])
-def test_ladder_golden(yb, golden, tag, stages, nh):
+@pytest.mark.parametrize('stages,nh', [(16, [2, 2]), (24, [3, 3])])
+def test_ladder_block_thomas_vs_oracle(yb, stages, nh):
+    """The same reductions through the block-Thomas engine (block-tridiagonal core solved block by block: the
+    engine of config 5 at full size, forced here at oracle-checkable sizes)."""
+    from oracle import hb_oracle as ho
+    y = yb.Netlist('ladder')
+    h = circuits.ladder(y, stages=stages, cje=0.0)
+    hb = mthb('HB1', h['freq'], nh)
+    hb.block_thomas = True
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert hb._plan.engine() == 'staged-block-thomas'
+    yo = ho.FlatNetlist()
+    circuits.ladder(yo, stages=stages, cje=0.0)
+    o = ho.HBOracle('HB1', h['freq'], nh)
+    conv_o = o.run(yo)[0]
+    assert conv == conv_o
+    assert hb.last.levels() == [l[1] for l in o.level_log]
+    assert relmax(hb.V, o.V) < 1e-9
+
+
+@pytest.mark.parametrize('tag,stages,nh,bt', [('ladder32_4x4', 32, [4, 4], None), ('ladder64_2x2', 64, [2, 2], None),
+                                              ('ladder32_4x4', 32, [4, 4], True), ('ladder64_2x2', 64, [2, 2], True)])
+def test_ladder_golden(yb, golden, tag, stages, nh, bt):
     """SURVEY 8d's oracle-checkable reductions of config 5, against the unmodified reference."""
     import os
     from conftest import GOLDEN
@@ -438,7 +459,9 @@ def test_ladder_golden(yb, golden, tag, stages, nh):
     y = yb.Netlist('ladder')
     h = circuits.ladder(y, stages=stages, cje=0.0)
     hb = mthb('HB1', h['freq'], nh)
+    hb.block_thomas = bt
     conv, freqs, Vf, _, _ = hb.run(y)
+    assert hb._plan.engine() == ('staged-block-thomas' if bt else 'staged-banded')
     assert conv == bool(g['converged'])
     assert hb.last.levels() == g['iters'].tolist()
     if conv:

@@ -32,6 +32,8 @@ class MultiToneHarmonicBalance:
         self.engine = 'auto'          # 'auto': fused on-chip engine when the circuit fits one SM; 'staged': HBM Jacobian
         self.peel = True              # eliminate ideal-source rows symbolically before the dense factorisation
         self.band = True              # staged engine: band storage for block-banded cores (chains of nodes)
+        self.block_thomas = None      # staged engine, block-tridiagonal cores: None = block-by-block solve for large
+                                      # blocks (S >= 128), True / False = always / never
         self.distributed = False      # run_batch / run_sweep: shard the circuits over torch.distributed ranks, gather
         self.last = None              # BatchResult of the last call
 
@@ -39,7 +41,9 @@ class MultiToneHarmonicBalance:
     def _flags(self):
         return ((L.FLAG_PNP_EXTENSION if self.pnp_extension else 0) | (L.FLAG_EXACT_JACOBIAN if self.exact_jacobian else 0) |
                 (0 if self.peel else L.FLAG_NO_PEEL) | (L.FLAG_STAGED if self.engine == 'staged' else 0) |
-                (0 if self.band else L.FLAG_NO_BAND))
+                (0 if self.band else L.FLAG_NO_BAND) |
+                (L.FLAG_BLOCK_THOMAS if self.block_thomas else 0) |
+                (L.FLAG_NO_BLOCK_THOMAS if self.block_thomas is False else 0))
 
     def _setup(self, netlist):
         self.netlist = netlist.copy()

@@ -68,6 +68,10 @@ class Plan:
         """half bandwidth (matrix elements) of the staged engine's band storage, 0 = dense core"""
         return int(L.lib().yhb_plan_band(self.handle))
 
+    def engine(self):
+        """'fused' | 'staged-dense' | 'staged-banded' | 'staged-block-thomas': the engine yhb_solve runs for this plan"""
+        return L.ENGINES[int(L.lib().yhb_plan_engine(self.handle))]
+
     def freqs(self, f1, f2=0.0):
         out = np.zeros(self.K + 1)
         L.check(L.lib().yhb_plan_freqs(self.handle, float(f1), float(f2), out.ctypes.data_as(C.POINTER(C.c_double))))

@@ -1,7 +1,9 @@
 // libyhb.so -- C ABI (include/yhb.h) over the staged harmonic-balance kernels.
 // Host side: plan compilation (stamp tables), workspace carving, and the launch loop that plays
 // run() / hb_loop (yalrf/Analyses/MultiToneHarmonicBalance.py:234-631) for a whole batch.
+#include <cublas_v2.h>
 #include <cuda_runtime.h>
+#include <cusolverDn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -141,6 +143,13 @@ struct yhb_plan : public yhb::Plan {
     void *hbuf;
     size_t hbuf_bytes;
     std::mutex mu;
+    // block-Thomas engine: library handles and scratch, created on first use
+    cublasHandle_t blas;
+    cusolverDnHandle_t solver;
+    double *btd_work;
+    int btd_lwork;
+    int *btd_ipiv, *btd_info;
+    std::vector<int> btd_list;
 };
 
 extern "C" const char *yhb_last_error(void) { return g_err.c_str(); }
@@ -429,6 +438,9 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
         const int kl = (bwn + 1) * S - 1;
         // worth band storage when the band (3 kl + 1 per row) is well below the dense row
         d.band = (!(desc->flags & YHB_FLAG_NO_BAND) && d.Nc > 0 && (long)3 * kl + 1 < (long)d.Wc / 2) ? kl : 0;
+        // block tridiagonal with blocks too large for the one-CTA banded elimination (or on request): block-Thomas
+        d.btd = (bwn <= 1 && d.Nc >= 3 && !(desc->flags & YHB_FLAG_NO_BLOCK_THOMAS) &&
+                 ((desc->flags & YHB_FLAG_BLOCK_THOMAS) || S >= 128)) ? 1 : 0;
     }
     d.nA = (int)a_row.size();
     d.nB = (int)b_row.size();
@@ -539,6 +551,12 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     pl->nl_index_dev = upload(pl, pl->nl_index);
     ok = ok && pl->lin_nodes_dev && pl->nl_kind_dev && pl->nl_index_dev;
     pl->pinned_counts = nullptr;
+    pl->blas = nullptr;
+    pl->solver = nullptr;
+    pl->btd_work = nullptr;
+    pl->btd_lwork = 0;
+    pl->btd_ipiv = nullptr;
+    pl->btd_info = nullptr;
     pl->own_stream = nullptr;
     pl->hbuf = nullptr;
     pl->hbuf_bytes = 0;
@@ -557,6 +575,11 @@ extern "C" void yhb_plan_destroy(yhb_plan *pl) {
     for (void *p : pl->allocs) cudaFree(p);
     if (pl->pinned_counts) cudaFreeHost(pl->pinned_counts);
     if (pl->hbuf) cudaFree(pl->hbuf);
+    if (pl->btd_work) cudaFree(pl->btd_work);
+    if (pl->btd_ipiv) cudaFree(pl->btd_ipiv);
+    if (pl->btd_info) cudaFree(pl->btd_info);
+    if (pl->blas) cublasDestroy(pl->blas);
+    if (pl->solver) cusolverDnDestroy(pl->solver);
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
     delete pl;
 }
@@ -571,6 +594,13 @@ extern "C" int yhb_plan_dims(const yhb_plan *pl, int32_t *N, int32_t *K, int32_t
 }
 
 extern "C" int yhb_plan_band(const yhb_plan *pl) { return pl ? pl->d.band : -1; }
+
+extern "C" int yhb_plan_engine(const yhb_plan *pl) {
+    if (!pl) { set_error("null plan"); return -1; }
+    if (fused_choice(pl->d).ok) return 0;
+    if (pl->d.btd) return 3;
+    return pl->d.band > 0 ? 2 : 1;
+}
 
 extern "C" int yhb_plan_core(const yhb_plan *pl, int32_t *Nc, int32_t *Wc, int32_t *fused) {
     if (!pl) { set_error("null plan"); return -1; }
@@ -639,7 +669,9 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.scratch = c.take<double>(L.eval_smem ? 1 : (size_t)B * esd);
     L.fc = fused_choice(d);
     L.fused = L.fc.ok;
-    ws.j_stride = L.fused ? 0 : (d.band > 0 ? (size_t)d.Wc * band_ld(d.band) : (size_t)d.Wc * d.Wc);
+    ws.j_stride = L.fused ? 0
+                  : d.btd ? (size_t)3 * d.Nc * d.S * d.S
+                          : (d.band > 0 ? (size_t)d.Wc * band_ld(d.band) : (size_t)d.Wc * d.Wc);
     ws.J = c.take<double>(L.fused ? 1 : (size_t)B * ws.j_stride);
     ws.x_stride = W + newton_scratch_doubles(d);
     ws.xstep = c.take<double>(L.fused ? 1 : B * ws.x_stride);
@@ -736,9 +768,61 @@ int launch_finish(const yhb_plan *pl, Layout &L, const yhb_result *res, cudaStre
     return 0;
 }
 
+// Block-Thomas elimination of one circuit's block-tridiagonal core (blocks as k_assemble_btd laid them out), right-hand
+// side / solution in rhs[Wc]:
+//   forward, block row i:  D_i -= L_i U'_{i-1},  b_i -= L_i b'_{i-1};  D_i = P L U (partial pivoting inside the block);
+//                          U'_i = D_i^-1 U_i,  b'_i = D_i^-1 b_i
+//   backward:              x_i = b'_i - U'_i x_{i+1}
+// 4 2/3 S^3 flops per block row, 3/7 of them in the Schur-complement DGEMM (cuBLAS: FP64 tensor cores), the rest in
+// cuSOLVER getrf / getrs.  Library baseline of this engine: hand-written kernels for it are the next step.
+int block_thomas_solve(yhb_plan *pl, double *J, double *rhs, cudaStream_t st) {
+    const PlanDev &d = pl->d;
+    const int S = d.S, Nc = d.Nc;
+    if (!pl->blas) {
+        if (cublasCreate(&pl->blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return -2; }
+        if (cusolverDnCreate(&pl->solver) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed"); return -2; }
+        if (cusolverDnDgetrf_bufferSize(pl->solver, S, S, J, S, &pl->btd_lwork) != CUSOLVER_STATUS_SUCCESS) {
+            set_error("cusolverDnDgetrf_bufferSize failed");
+            return -2;
+        }
+        YHB_CUDA(cudaMalloc(&pl->btd_work, sizeof(double) * std::max(pl->btd_lwork, 1)));
+        YHB_CUDA(cudaMalloc(&pl->btd_ipiv, sizeof(int) * (size_t)S * Nc));
+        YHB_CUDA(cudaMalloc(&pl->btd_info, sizeof(int)));
+    }
+    cublasSetStream(pl->blas, st);
+    cusolverDnSetStream(pl->solver, st);
+    const double one = 1., minus = -1.;
+    const size_t bs = (size_t)S * S;
+    auto blkp = [&](int r, int which) { return J + ((size_t)r * 3 + which) * bs; };
+#define YHB_LIB(call, ok)                                                       \
+    do {                                                                        \
+        if ((call) != (ok)) { set_error(#call " failed"); return -2; }          \
+    } while (0)
+    for (int i = 0; i < Nc; ++i) {
+        double *D = blkp(i, 1), *b = rhs + (size_t)i * S;
+        int *ipiv = pl->btd_ipiv + (size_t)i * S;
+        if (i > 0) {
+            const double *Lo = blkp(i, 0), *Up = blkp(i - 1, 2);
+            YHB_LIB(cublasDgemm(pl->blas, CUBLAS_OP_N, CUBLAS_OP_N, S, S, S, &minus, Lo, S, Up, S, &one, D, S), CUBLAS_STATUS_SUCCESS);
+            YHB_LIB(cublasDgemv(pl->blas, CUBLAS_OP_N, S, S, &minus, Lo, S, b - S, 1, &one, b, 1), CUBLAS_STATUS_SUCCESS);
+        }
+        YHB_LIB(cusolverDnDgetrf(pl->solver, S, S, D, S, pl->btd_work, ipiv, pl->btd_info), CUSOLVER_STATUS_SUCCESS);
+        if (i + 1 < Nc)
+            YHB_LIB(cusolverDnDgetrs(pl->solver, CUBLAS_OP_N, S, S, D, S, ipiv, blkp(i, 2), S, pl->btd_info), CUSOLVER_STATUS_SUCCESS);
+        YHB_LIB(cusolverDnDgetrs(pl->solver, CUBLAS_OP_N, S, 1, D, S, ipiv, b, S, pl->btd_info), CUSOLVER_STATUS_SUCCESS);
+    }
+    for (int i = Nc - 2; i >= 0; --i) {
+        double *b = rhs + (size_t)i * S;
+        YHB_LIB(cublasDgemv(pl->blas, CUBLAS_OP_N, S, S, &minus, blkp(i, 2), S, b + S, 1, &one, b, 1), CUBLAS_STATUS_SUCCESS);
+    }
+#undef YHB_LIB
+    return 0;
+}
+
 // the Newton / continuation launch loop shared by yhb_solve and yhb_newton
-int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, Layout &L, int have_v0,
+int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, Layout &L, int have_v0,
              const double *alpha_fixed, const yhb_result *res, cudaStream_t st) {
+    yhb_plan *pl = const_cast<yhb_plan *>(cpl);  // library handles of the block-Thomas engine are created lazily
     const PlanDev &d = pl->d;
     const int B = p->batch;
     Workspace &ws = L.ws;
@@ -788,7 +872,33 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
         YHB_CUDA(cudaMemcpyAsync(hc, ws.count, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         YHB_CUDA(cudaStreamSynchronize(st));
         const int nsolve = hc[cur ^ 1];
-        if (nsolve > 0) {
+        if (nsolve > 0 && d.btd) {
+            // block-Thomas engine: peeled rows + rhs, blocks, block elimination (library calls), back-substitution
+            const size_t rowbuf = 4;
+            {
+                ProfScope ps(PK_LU, st);
+                k_solve_core<<<nsolve, 1024, rowbuf * sizeof(double), st>>>(d, ws, ea, cur ^ 1, 1);
+            }
+            {
+                dim3 ga(nsolve, 3 * d.Nc, (d.S * d.S + kBtdChunk - 1) / kBtdChunk);
+                ProfScope ps(PK_ASSEMBLE, st);
+                k_assemble_btd<<<ga, 256, 0, st>>>(d, ws, ea, cur ^ 1);
+            }
+            YHB_CUDA(cudaGetLastError());
+            pl->btd_list.resize(nsolve);
+            YHB_CUDA(cudaMemcpyAsync(pl->btd_list.data(), ws.list[cur ^ 1], nsolve * sizeof(int), cudaMemcpyDeviceToHost, st));
+            YHB_CUDA(cudaStreamSynchronize(st));
+            {
+                ProfScope ps(PK_LU, st);
+                for (int i = 0; i < nsolve; ++i) {
+                    const int b = pl->btd_list[i];
+                    if (int rc = block_thomas_solve(pl, ws.J + (size_t)b * ws.j_stride, ws.rhs + (size_t)b * (d.Wc + 1), st))
+                        return rc;
+                }
+                k_solve_core<<<nsolve, 1024, rowbuf * sizeof(double), st>>>(d, ws, ea, cur ^ 1, 2);
+            }
+            YHB_CUDA(cudaGetLastError());
+        } else if (nsolve > 0) {
             if (d.Wc > 0) {
                 dim3 ga(nsolve, (d.Wc + kAsmRows - 1) / kAsmRows);
                 ProfScope ps(PK_ASSEMBLE, st);
@@ -799,7 +909,7 @@ int run_loop(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, La
                 // large cores: the HBM-resident elimination is latency bound, more warps per circuit hide it
                 const int lu_threads = d.Wc >= 160 ? 1024 : kLuThreads;
                 const size_t rowbuf = d.band > 0 ? std::min<size_t>(d.Wc, 2 * (size_t)d.band + 1) + 3 : (size_t)d.Wc + 2;
-                k_solve_core<<<nsolve, lu_threads, rowbuf * sizeof(double), st>>>(d, ws, ea, cur ^ 1);
+                k_solve_core<<<nsolve, lu_threads, rowbuf * sizeof(double), st>>>(d, ws, ea, cur ^ 1, 0);
             }
             YHB_CUDA(cudaGetLastError());
         }

@@ -67,6 +67,8 @@ struct PlanDev {
     // Core: J[core_rows, core_cols] y = F[core_rows] - sum_{A-known m} J[row, m] dV[m].
     int Nc, Wc, nA, nB;
     int band;  // > 0: the core is block banded over nodes; kl = ku = band (in matrix elements), band storage
+    int btd;   // the core is block TRIdiagonal over nodes and is solved block by block (block-Thomas engine): the
+               // Jacobian is stored as Nc x 3 column-major S x S blocks (sub-diagonal, diagonal, super-diagonal)
     const int *core_rows, *core_cols;  // [Nc] node indices
     const int *core_col_of;            // [N] -> position among core_cols or -1
     const int *a_row, *a_col, *a_sgn;  // [nA]
