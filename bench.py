@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 
 GRID = 64
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused launch over the 4096-point grid (ncu --set full, profiles/)
-FUSED_TRAFFIC_BYTES = {'diffamp': 52365312, 'activeload': None}
+FUSED_TRAFFIC_BYTES = {'diffamp': 46917120, 'activeload': None}
 
 
 def grid_points(rank, world, workload):
@@ -279,13 +279,17 @@ def run_gpu(args):
             roof.update({'bound': 'tensor', 'achieved': ach, 'peak': float(peak[0]), 'unit': 'TFLOP/s',
                          'frac': ach / float(peak[0]), 'achieved_executed': ach_exec,
                          'traffic': FUSED_TRAFFIC_BYTES.get(args.workload),
-                         'note': 'FP64 pipe.  achieved = SURVEY 8d algorithmic LU flops (2/3 W^3 + 2 W^2, W=%d, the '
-                                 'system the reference hands to LAPACK) x factorisations / CUDA-event time of the '
-                                 'whole fused kernel (which also does device evaluation, DFTs and assembly); '
-                                 'achieved_executed counts the Wc=%d core that structural peeling leaves.  peak = '
-                                 'DFMA microbenchmark run live (MEASURED_PEAKS.json has no fp64 figure).  ncu: FP64 '
-                                 'pipe active 15 %%, issue slots 33 %% (profiles/).  traffic = dram bytes of one '
-                                 'launch from ncu --set full (profiles/).' % (W, wc)})
+                         'note': 'FP64 pipes (DFMA + DMMA).  achieved = SURVEY 8d algorithmic LU flops (2/3 W^3 + 2 W^2, '
+                                 'W=%d, the system the reference hands to LAPACK) x factorisations / CUDA-event time of '
+                                 'the whole fused kernel (which also does device evaluation, the DFTs, assembly and the '
+                                 'peeled rows); achieved_executed counts the Wc=%d core that structural peeling leaves '
+                                 '(the kernel executes Wc^3 multiply-adds per solve as a Gauss-Jordan elimination, its '
+                                 'trailing updates on the FP64 tensor pipe).  peak = DFMA microbenchmark run live '
+                                 '(MEASURED_PEAKS.json has no fp64 figure; DMMA m8n8k4 measured at 36.8 TFLOP/s, '
+                                 'profiles/r01_microbench.txt).  ncu (profiles/r01_bench_fused_full.txt): DMMA pipe '
+                                 'active 8.8 %%, FP64 pipe 5.1 %%, issue slots 28 %%: the kernel is bound by the serial '
+                                 'pivot chain at 2 resident circuits per SM.  traffic = dram bytes of one launch from '
+                                 'ncu --set full.' % (W, wc)})
         else:
             hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(
                 os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
