@@ -47,6 +47,42 @@ def test_dc_vs_oracle(yb, name):
     assert np.max(np.abs(x[:n, 0] - xo[:n, 0])) <= 1e-10 * max(1.0, np.max(np.abs(xo[:n, 0])))
 
 
+def test_dc_engines_bit_identical(yb, monkeypatch):
+    """The one-warp DC engine (k_dc_warp: junction-per-lane evaluation, entry-parallel ordered stamping, register
+    Gaussian elimination) against the general engine (k_dc) on a bias sweep whose points need plain Newton, source
+    stepping and many limiter-bound iterations: bit-identical operating points, identical Newton iteration counts,
+    and the oracle's counts (DC.py:125-279)."""
+    from oracle import hb_oracle as ho
+    from yalrf_b200 import _engine as E
+    from yalrf_b200._flatten import ParamBlock
+    from yalrf_b200.Analyses.DC import dc_solve_batch
+    for build, dev_keys, lo, hi in [(circuits.diffamp, ('i3', 'i5'), 1.0, 1.4), (circuits.diffamp_activeload, ('i3', 'i5'), 1.3, 1.7)]:
+        y = yb.Netlist('x')
+        h = build(y)
+        n = 48
+        vb = np.linspace(lo, hi, n)
+        plan, topo = E.get_plan(y, h['freq'], h['K'])
+        pb = ParamBlock(topo, h['freq'], n)
+        for k in dev_keys:
+            pb.set(h[k], 'dc', vb)
+        monkeypatch.delenv('YHB_DC_ENGINE', raising=False)
+        v_warp, i_warp = dc_solve_batch(plan, pb)
+        monkeypatch.setenv('YHB_DC_ENGINE', 'block')
+        v_blk, i_blk = dc_solve_batch(plan, pb)
+        monkeypatch.delenv('YHB_DC_ENGINE', raising=False)
+        assert np.array_equal(i_warp, i_blk)
+        assert np.array_equal(v_warp.view(np.int64), v_blk.view(np.int64))
+        assert i_warp[:, 0].all()
+        for j in (0, 17, 47):
+            yo = ho.FlatNetlist()
+            build(yo, vbias=vb[j])
+            o = ho.DCOracle(yo)
+            o.total_newton = 0
+            xo = o.run()
+            assert o.total_newton == i_warp[j, 1]
+            assert np.max(np.abs(v_warp[j] - xo[:plan.N, 0])) <= 1e-10 * max(1.0, np.max(np.abs(xo[:plan.N, 0])))
+
+
 # ----------------------------------------------------------------------------- config 1
 @pytest.mark.parametrize('tag,ac,opts', [('hb_diode', 5.0, {}), ('hb_diode_tight', 5.0, {'reltol': 1e-9, 'abstol': 1e-12}),
                                          ('hb_diode_ac0p5', 0.5, {}), ('hb_diode_ac2', 2.0, {})])

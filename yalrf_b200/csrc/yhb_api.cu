@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -137,6 +138,9 @@ using namespace yhb;
 struct yhb_plan : public yhb::Plan {
     std::vector<int> nl_kind, nl_index;
     const int *nl_kind_dev, *nl_index_dev;
+    // one-warp DC engine tables (build_dc_tables); dc_warp = the circuit qualifies
+    const int *dc_ent_dev, *dc_lane_dev;
+    int dc_warp, dc_ent_ints;
     int *pinned_counts;
     cudaStream_t own_stream;
     // yhb_run_host buffers
@@ -194,6 +198,77 @@ extern "C" int yhb_profile_read(int64_t *launches, double *ms) {
         if (ms) ms[i] = g_prof.ms[i];
     }
     return 0;
+}
+
+// Plan-time tables of the one-warp DC engine (k_dc_warp): the role of every lane in the device evaluation (a BJT
+// takes two lanes, one per junction) and, per entry of [A | z], its contributions in the order dc_apply_stamps
+// adds them (netlist order, then stamp order within the device).
+static bool build_dc_tables(yhb_plan *pl) {
+    const PlanDev &d = pl->d;
+    const int M = d.N + pl->num_inductors;
+    const int nnl = (int)pl->nl_kind.size();
+    int lanes = 0;
+    for (int t = 0; t < nnl; ++t) lanes += pl->nl_kind[t] == 1 ? 2 : 1;
+    pl->dc_warp = M <= 24 && lanes <= 32;
+    pl->dc_ent_dev = pl->dc_lane_dev = nullptr;
+    pl->dc_ent_ints = 0;
+    if (!pl->dc_warp) return true;
+    std::vector<int> lane_tab(32 * kDcLaneInts, 0);
+    for (int l = 0; l < 32; ++l) { lane_tab[l * kDcLaneInts] = -1; lane_tab[l * kDcLaneInts + 7] = l; }
+    std::vector<std::vector<int>> ent((size_t)M * M + M);
+    auto addA = [&](int r, int c, int t, int slot, int neg) {
+        if (r > 0 && c > 0) ent[(size_t)(r - 1) * M + (c - 1)].push_back(((t * kDcOut + slot) << 1) | neg);
+    };
+    auto addz = [&](int r, int t, int slot, int neg) {
+        if (r > 0) ent[(size_t)M * M + (r - 1)].push_back(((t * kDcOut + slot) << 1) | neg);
+    };
+    int l = 0;
+    for (int t = 0; t < nnl; ++t) {
+        const int kind = pl->nl_kind[t], idx = pl->nl_index[t];
+        if (kind == 1) {
+            const int B = pl->bjt_nodes[3 * idx], C = pl->bjt_nodes[3 * idx + 1], E = pl->bjt_nodes[3 * idx + 2];
+            for (int h = 0; h < 2; ++h, ++l) {
+                int *q = &lane_tab[l * kDcLaneInts];
+                q[0] = 1; q[1] = h; q[2] = t; q[3] = idx; q[4] = B; q[5] = C; q[6] = E; q[7] = h ? l - 1 : l + 1;
+            }
+            const int rc[3] = {B, C, E};
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) addA(rc[i], rc[j], t, 3 * i + j, 0);
+            for (int i = 0; i < 3; ++i) addz(rc[i], t, 9 + i, 0);
+        } else {
+            const int *nodes = kind == 0 ? &pl->diode_nodes[2 * idx] : &pl->cubic_nodes[2 * idx];
+            const int n1 = nodes[0], n2 = nodes[1];
+            int *q = &lane_tab[l * kDcLaneInts];
+            q[0] = kind; q[1] = 0; q[2] = t; q[3] = idx; q[4] = n1; q[5] = n2; q[6] = 0; q[7] = l;
+            ++l;
+            addA(n1, n1, t, 0, 0);  // dc_stamp2
+            addA(n2, n2, t, 0, 0);
+            if (n1 > 0 && n2 > 0) {
+                addA(n1, n2, t, 0, 1);
+                addA(n2, n1, t, 0, 1);
+            }
+            addz(n1, t, 1, 1);
+            addz(n2, t, 1, 0);
+        }
+    }
+    const int NE = (int)ent.size(), LD = (M + 1) | 1;
+    std::vector<int> tab(NE + 1, 0), dst(NE), items;
+    for (int e = 0; e < NE; ++e) {
+        items.insert(items.end(), ent[e].begin(), ent[e].end());
+        tab[e + 1] = (int)items.size();
+        if (e < M * M) {
+            const int r = e / M, c = e % M;
+            dst[e] = (r * LD + c) | ((r == c && r < d.N) ? 1 << 16 : 0);
+        } else {
+            dst[e] = (e - M * M) * LD + M;
+        }
+    }
+    tab.insert(tab.end(), dst.begin(), dst.end());
+    tab.insert(tab.end(), items.begin(), items.end());
+    pl->dc_ent_ints = (int)tab.size();
+    pl->dc_ent_dev = upload(pl, tab);
+    pl->dc_lane_dev = upload(pl, lane_tab);
+    return pl->dc_ent_dev && pl->dc_lane_dev;
 }
 
 extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
@@ -547,6 +622,7 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
         }
     }
     pl->lin_nodes_dev = upload(pl, pl->lin_nodes);
+    ok = ok && build_dc_tables(pl);
     pl->nl_kind_dev = upload(pl, pl->nl_kind);
     pl->nl_index_dev = upload(pl, pl->nl_index);
     ok = ok && pl->lin_nodes_dev && pl->nl_kind_dev && pl->nl_index_dev;
@@ -948,14 +1024,29 @@ extern "C" int yhb_dc_solve(const yhb_plan *pl, const yhb_params *p, void *wsbuf
     a.stride = L.ws.dc_stride;
     a.Vdc = Vdc ? Vdc : L.ws.dcV;
     a.info = dc_info ? dc_info : L.ws.dcinfo;
+    a.ent_tab = pl->dc_ent_dev;
+    a.ent_ints = pl->dc_ent_ints;
+    a.lane_tab = pl->dc_lane_dev;
     cudaStream_t st = (cudaStream_t)stream;
+    // YHB_DC_ENGINE=block forces the general engine (A/B runs, parity tests of the one-warp engine against it)
+    const char *dc_env = getenv("YHB_DC_ENGINE");  // read per call: tests flip it within one process
+    const bool force_block = dc_env && !strcmp(dc_env, "block");
+    if (pl->dc_warp && !force_block) {
+        const int LD = (a.M + 1) | 1;
+        const size_t smw = ((size_t)a.M * a.M + a.M + (size_t)kDcOut * std::max(a.nnl, 1) + (size_t)a.M * LD) * sizeof(double) +
+                           (size_t)a.ent_ints * sizeof(int);
+        ProfScope ps(PK_DC, st);
+        if (a.M <= 12) k_dc_warp<12><<<p->batch, 32, smw, st>>>(d, a, p->batch);
+        else k_dc_warp<24><<<p->batch, 32, smw, st>>>(d, a, p->batch);
+        YHB_CUDA(cudaGetLastError());
+        return 0;
+    }
     size_t dsm = (a.M + 2) * sizeof(double);
     a.use_smem = (dsm + a.stride * sizeof(double)) <= 40 * 1024;  // small circuits: the whole DC analysis on chip
     if (a.use_smem) dsm += a.stride * sizeof(double);
     {
         ProfScope ps(PK_DC, st);
-        const int threads = (a.M <= 24 && a.nnl <= 32) ? 32 : kDcThreads;
-        k_dc<<<p->batch, threads, dsm, st>>>(d, a, p->batch);
+        k_dc<<<p->batch, kDcThreads, dsm, st>>>(d, a, p->batch);
     }
     YHB_CUDA(cudaGetLastError());
     return 0;
@@ -1105,9 +1196,8 @@ __global__ void k_stage_ifft(PlanDev P, int batch, const double *V, double *vt) 
 // per sample).  Persistent CTAs walk chunks of kDevChunk circuits: the hoisted model constants of the chunk are
 // derived into shared memory by one thread per (circuit, device), then one thread per (circuit, device, sample)
 // evaluates; loads and stores are contiguous along the sample index.
-constexpr int kDevChunk = 32;
-
-__global__ void __launch_bounds__(256, 2) k_stage_device_eval(PlanDev P, int batch, const double *diode_par,
+template <int kDevChunk, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_stage_device_eval(PlanDev P, int batch, const double *diode_par,
                                                               const double *bjt_par, const double *cubic_par,
                                                               const double *vt, const double *vtprev, double *diode_out,
                                                               double *bjt_out, double *cubic_out) {
@@ -1179,20 +1269,31 @@ extern "C" int yhb_stage_device_eval(const yhb_plan *pl, const yhb_params *p, co
         set_error("missing array");
         return -1;
     }
-    size_t smem = (size_t)kDevChunk * (d.nd * sizeof(DiodeDerived) + d.nb * sizeof(BjtDerived));
-    if (smem > 200 * 1024) { set_error("too many devices for the stage kernel"); return -1; }
-    if (smem > 48 * 1024)
-        YHB_CUDA(cudaFuncSetAttribute(k_stage_device_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     YHB_CUDA(cudaGetDevice(&dev));
     YHB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int chunks = (p->batch + kDevChunk - 1) / kDevChunk;
-    const int grid = std::min(chunks, 2 * sms);  // persistent: 2 resident CTAs per SM
-    k_stage_device_eval<<<grid, 256, smem, (cudaStream_t)stream>>>(d, p->batch, p->diode_par, p->bjt_par,
-                                                                   p->cubic_par, vt, vtprev, diode_out, bjt_out,
-                                                                   cubic_out);
-    YHB_CUDA(cudaGetLastError());
-    return 0;
+    // variant = chunk size (circuits per work item) and resident CTAs per SM; YHB_DEVSTAGE picks one for A/B runs
+    static const int variant = getenv("YHB_DEVSTAGE") ? atoi(getenv("YHB_DEVSTAGE")) : 0;
+    auto launch = [&](auto kern, int chunk, int minb) -> int {
+        size_t smem = (size_t)chunk * (d.nd * sizeof(DiodeDerived) + d.nb * sizeof(BjtDerived));
+        if (smem > 200 * 1024) { set_error("too many devices for the stage kernel"); return -1; }
+        if (smem > 48 * 1024)
+            YHB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int chunks = (p->batch + chunk - 1) / chunk;
+        const int grid = std::min(chunks, minb * sms);  // persistent CTAs
+        kern<<<grid, 256, smem, (cudaStream_t)stream>>>(d, p->batch, p->diode_par, p->bjt_par, p->cubic_par, vt, vtprev,
+                                                        diode_out, bjt_out, cubic_out);
+        YHB_CUDA(cudaGetLastError());
+        return 0;
+    };
+    switch (variant) {
+        case 1: return launch(k_stage_device_eval<8, 2>, 8, 2);
+        case 2: return launch(k_stage_device_eval<8, 3>, 8, 3);
+        case 3: return launch(k_stage_device_eval<8, 4>, 8, 4);
+        case 4: return launch(k_stage_device_eval<4, 3>, 4, 3);
+        case 5: return launch(k_stage_device_eval<16, 3>, 16, 3);
+        default: return launch(k_stage_device_eval<32, 2>, 32, 2);
+    }
 }
 
 extern "C" int yhb_stage_assemble(const yhb_plan *pl, const yhb_params *p, void *wsbuf, size_t ws_bytes, const double *V,

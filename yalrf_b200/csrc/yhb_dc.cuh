@@ -6,11 +6,21 @@
 // Stamping is done by one thread in netlist order (it fixes the floating-point summation order);
 // the linear solves use the CTA-wide elimination of yhb_kernels.cuh.
 #pragma once
+#include <type_traits>
+
 #include "yhb_kernels.cuh"
 
 namespace yhb {
 
-constexpr int kDcThreads = 128;  // upper bound; tiny circuits run one warp per circuit
+#ifdef YHB_TIMING
+#define YHB_T0_() tmark = clock64()
+#define YHB_TACC_(slot) do { unsigned long long n__ = clock64(); atomicAdd(&g_timing[slot], n__ - tmark); tmark = n__; } while (0)
+#else
+#define YHB_T0_() do {} while (0)
+#define YHB_TACC_(slot) do {} while (0)
+#endif
+
+constexpr int kDcThreads = 128;  // general engine (k_dc); small circuits run on the one-warp engine (k_dc_warp)
 
 struct DcArgs {
     const double *lin_val, *src_val, *diode_par, *bjt_par, *cubic_par;
@@ -24,55 +34,71 @@ struct DcArgs {
     int use_smem;
     double *Vdc;           // [B][N]
     int *info;             // [B][2] converged, Newton iterations
+    // one-warp engine (k_dc_warp): plan-time tables, see build_dc_tables() in yhb_api.cu
+    const int *ent_tab;    // [NE + 1] CSR pointers over the NE = M*M + M entries of [A | z] (row-major A, then z),
+                           // [NE] destination in the work matrix (row * LD + col) | diagonal-of-a-node flag << 16,
+                           // [items] contributions in stamping order: ((t * kDcOut + slot) << 1) | negate
+    int ent_ints;
+    const int *lane_tab;   // [32][kDcLaneInts] role of every lane in the device evaluation
 };
 
-constexpr int kDcOut = 12;  // per-device stamp values handed from the parallel evaluation to the ordered stamping
+constexpr int kDcOut = 12;
+constexpr int kDcLaneInts = 8;  // kind (-1 none), half, t, idx, n1, n2, n3, partner lane  // per-device stamp values handed from the parallel evaluation to the ordered stamping
 
 __host__ __device__ inline size_t dc_scratch_doubles(int M, int nd, int nb, int nc) {
     return (size_t)3 * M * M + (size_t)7 * M + 3 * nd + 2 * nb + (size_t)kDcOut * (nd + nb + nc) + 8;
 }
 
-// Gaussian elimination with partial pivoting on [A | rhs] by ONE warp, n <= 32: rows live on lanes during the
-// elimination (each lane walks its own row), columns live on lanes during the row interchange.  Same pivot rule
-// and arithmetic as block_ge_solve (dgetf2-style reciprocal scaling); only __syncwarp, no block barrier.
-__device__ inline void warp_ge_solve(double *A, int lda, double *rhs, double *x, int n) {
-    const int lane = threadIdx.x & 31;
-    for (int k = 0; k < n; ++k) {
-        const double v = (lane >= k && lane < n) ? fabs(A[(size_t)lane * lda + k]) : -1.;
-        const unsigned long long bits = v < 0. ? 0ull : (unsigned long long)__double_as_longlong(v);
-        const bool valid = lane >= k && lane < n;
-        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
-        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
-        int p = __reduce_min_sync(0xffffffffu, (valid && hi == mhi && lo == mlo) ? lane : 0x7fffffff);
-        if (p == 0x7fffffff) p = k;
-        if (p != k) {
-            for (int j = k + lane; j <= n; j += 32) {
-                double *pk = (j < n) ? &A[(size_t)k * lda + j] : &rhs[k];
-                double *pp = (j < n) ? &A[(size_t)p * lda + j] : &rhs[p];
-                const double t = *pk;
-                *pk = *pp;
-                *pp = t;
-            }
+// linear stamps in netlist order (DC.py:79-87) into zeroed (A, z); one thread
+__device__ inline void dc_stamp_linear(const PlanDev &P, const DcArgs &a, int b, double *A, double *z, int M) {
+    const int N = P.N;
+    const double *lv = a.lin_val + (size_t)b * P.nlin * 2;
+    int branch = N;
+    for (int e = 0; e < P.nlin; ++e) {
+        const int *nd = a.lin_nodes + 4 * e;
+        const int n1 = nd[0], n2 = nd[1], n3 = nd[2], n4 = nd[3];
+        const double v = lv[2 * e];
+        switch (P.lin_kind[e]) {
+            case YHB_LIN_RESISTOR: {  // Resistor.py:30-35
+                double g = 1.0 / v;
+                double dummy[1];
+                (void)dummy;
+                if (n1 > 0) A[(size_t)(n1 - 1) * M + n1 - 1] += g;
+                if (n2 > 0) A[(size_t)(n2 - 1) * M + n2 - 1] += g;
+                if (n1 > 0 && n2 > 0) {
+                    A[(size_t)(n1 - 1) * M + n2 - 1] -= g;
+                    A[(size_t)(n2 - 1) * M + n1 - 1] -= g;
+                }
+            } break;
+            case YHB_LIN_INDUCTOR: {  // Inductor.py:21-26 (one branch row per inductor)
+                int i = branch++;
+                if (n1 > 0) { A[(size_t)(n1 - 1) * M + i] = +1.0; A[(size_t)i * M + n1 - 1] = +1.0; }
+                if (n2 > 0) { A[(size_t)(n2 - 1) * M + i] = -1.0; A[(size_t)i * M + n2 - 1] = -1.0; }
+            } break;
+            case YHB_LIN_GYRATOR: {  // Gyrator.py:22-30 (uses G at DC)
+#define YHB_G(r, cc, s) do { if ((r) > 0 && (cc) > 0) A[(size_t)((r) - 1) * M + (cc) - 1] += (s) * v; } while (0)
+                YHB_G(n1, n2, +1.);
+                YHB_G(n1, n3, -1.);
+                YHB_G(n2, n1, -1.);
+                YHB_G(n2, n4, +1.);
+                YHB_G(n3, n1, +1.);
+                YHB_G(n3, n4, -1.);
+                YHB_G(n4, n2, -1.);
+                YHB_G(n4, n3, +1.);
+#undef YHB_G
+            } break;
+            default:  // capacitor (Capacitor.py:30-31), ihf (IdealHarmonicFilter.py:23-24): open at DC
+                break;
         }
-        __syncwarp();
-        const double rinv = 1. / A[(size_t)k * lda + k];
-        if (lane > k && lane < n) {
-            double *ai = A + (size_t)lane * lda;
-            const double *ak = A + (size_t)k * lda;
-            const double l = -(ai[k] * rinv);
-            for (int j = k + 1; j < n; ++j) ai[j] = fma(l, ak[j], ai[j]);
-            rhs[lane] = fma(l, rhs[k], rhs[lane]);
-        }
-        __syncwarp();
     }
-    for (int j = n - 1; j >= 0; --j) {
-        const double xj = rhs[j] / A[(size_t)j * lda + j];
-        __syncwarp();
-        if (lane < j) rhs[lane] = fma(-A[(size_t)lane * lda + j], xj, rhs[lane]);
-        if (lane == 0) x[j] = xj;
-        __syncwarp();
+    const double *sv = a.src_val + (size_t)b * P.nsrc * 3;
+    for (int s = 0; s < P.nsrc; ++s) {  // CurrentSource.py:23-26
+        if (P.src_kind[s] != YHB_SRC_DC && P.src_kind[s] != YHB_SRC_DC_ONLY) continue;
+        int n1 = P.src_nodes[2 * s], n2 = P.src_nodes[2 * s + 1];
+        if (n1 > 0) z[n1 - 1] = z[n1 - 1] + sv[3 * s];
+        if (n2 > 0) z[n2 - 1] = z[n2 - 1] - sv[3 * s];
     }
+    for (int i = 0; i < N; ++i) A[(size_t)i * M + i] += 1e-12;  // DC.py:86-87
 }
 
 struct DcCtx {
@@ -293,13 +319,16 @@ __device__ inline bool dc_newton(DcCtx &c, double extra_g, double zscale, const 
     int k = 0;
     bool converged = false;
     while (!converged && k < maxiter) {
+        YHB_T0();
         for (int i = tid; i < M * M; i += nt) c.Anl[i] = 0.;
         for (int i = tid; i < M; i += nt) c.znl[i] = 0.;
         __syncthreads();
         dc_eval_devices(c, c.xk);
         __syncthreads();
+        if (tid == 0) YHB_TACC(24);
         if (tid == 0) dc_apply_stamps(c);
         __syncthreads();
+        if (tid == 0) YHB_TACC(25);
         for (int i = tid; i < M * M; i += nt) {
             int r = i / M, cc = i - r * M;
             double a = c.A[i];
@@ -308,13 +337,10 @@ __device__ inline bool dc_newton(DcCtx &c, double extra_g, double zscale, const 
         }
         for (int i = tid; i < M; i += nt) c.zw[i] = zscale * c.z[i] + c.znl[i];
         __syncthreads();
-        if (nt == 32) {
-            warp_ge_solve(c.Aw, M, c.zw, c.x, M);
-            __syncthreads();
-        } else {
-            block_ge_solve(c.Aw, M, c.zw, c.x, M, c.s_row, c.s_val, c.s_idx);
-        }
+        if (tid == 0) YHB_TACC(26);
+        block_ge_solve(c.Aw, M, c.zw, c.x, M, c.s_row, c.s_val, c.s_idx);
         c.newton += 1;
+        if (tid == 0) YHB_TACC(27);
         int nan = 0;
         for (int i = tid; i < M; i += nt) nan |= isnan(c.x[i]);
         if (__syncthreads_or(nan)) return false;  // Solver.py:14
@@ -328,6 +354,7 @@ __device__ inline bool dc_newton(DcCtx &c, double extra_g, double zscale, const 
             k = k + 1;
         }
         __syncthreads();
+        if (tid == 0) YHB_TACC(28);
     }
     return converged;
 }
@@ -369,55 +396,7 @@ __global__ void __launch_bounds__(kDcThreads) k_dc(PlanDev P, DcArgs a, int batc
     for (int i = tid; i < M; i += nt) { c.z[i] = 0.; c.x0[i] = 0.; c.x[i] = 0.; }
     for (int i = tid; i < 3 * P.nd + 2 * P.nb; i += nt) c.dst[i] = 0.;  // Diode.init / BJT.init
     __syncthreads();
-    if (tid == 0) {  // linear stamps in netlist order, DC.py:79-87
-        const double *lv = a.lin_val + (size_t)b * P.nlin * 2;
-        int branch = N;
-        for (int e = 0; e < P.nlin; ++e) {
-            const int *nd = a.lin_nodes + 4 * e;
-            const int n1 = nd[0], n2 = nd[1], n3 = nd[2], n4 = nd[3];
-            const double v = lv[2 * e];
-            switch (P.lin_kind[e]) {
-                case YHB_LIN_RESISTOR: {  // Resistor.py:30-35
-                    double g = 1.0 / v;
-                    double dummy[1];
-                    (void)dummy;
-                    if (n1 > 0) c.A[(size_t)(n1 - 1) * M + n1 - 1] += g;
-                    if (n2 > 0) c.A[(size_t)(n2 - 1) * M + n2 - 1] += g;
-                    if (n1 > 0 && n2 > 0) {
-                        c.A[(size_t)(n1 - 1) * M + n2 - 1] -= g;
-                        c.A[(size_t)(n2 - 1) * M + n1 - 1] -= g;
-                    }
-                } break;
-                case YHB_LIN_INDUCTOR: {  // Inductor.py:21-26 (one branch row per inductor)
-                    int i = branch++;
-                    if (n1 > 0) { c.A[(size_t)(n1 - 1) * M + i] = +1.0; c.A[(size_t)i * M + n1 - 1] = +1.0; }
-                    if (n2 > 0) { c.A[(size_t)(n2 - 1) * M + i] = -1.0; c.A[(size_t)i * M + n2 - 1] = -1.0; }
-                } break;
-                case YHB_LIN_GYRATOR: {  // Gyrator.py:22-30 (uses G at DC)
-#define YHB_G(r, cc, s) do { if ((r) > 0 && (cc) > 0) c.A[(size_t)((r) - 1) * M + (cc) - 1] += (s) * v; } while (0)
-                    YHB_G(n1, n2, +1.);
-                    YHB_G(n1, n3, -1.);
-                    YHB_G(n2, n1, -1.);
-                    YHB_G(n2, n4, +1.);
-                    YHB_G(n3, n1, +1.);
-                    YHB_G(n3, n4, -1.);
-                    YHB_G(n4, n2, -1.);
-                    YHB_G(n4, n3, +1.);
-#undef YHB_G
-                } break;
-                default:  // capacitor (Capacitor.py:30-31), ihf (IdealHarmonicFilter.py:23-24): open at DC
-                    break;
-            }
-        }
-        const double *sv = a.src_val + (size_t)b * P.nsrc * 3;
-        for (int s = 0; s < P.nsrc; ++s) {  // CurrentSource.py:23-26
-            if (P.src_kind[s] != YHB_SRC_DC && P.src_kind[s] != YHB_SRC_DC_ONLY) continue;
-            int n1 = P.src_nodes[2 * s], n2 = P.src_nodes[2 * s + 1];
-            if (n1 > 0) c.z[n1 - 1] = c.z[n1 - 1] + sv[3 * s];
-            if (n2 > 0) c.z[n2 - 1] = c.z[n2 - 1] - sv[3 * s];
-        }
-        for (int i = 0; i < N; ++i) c.A[(size_t)i * M + i] += 1e-12;  // DC.py:86-87
-    }
+    if (tid == 0) dc_stamp_linear(P, a, b, c.A, c.z, M);
     __syncthreads();
 
     bool solved = false;
@@ -493,6 +472,395 @@ __global__ void __launch_bounds__(kDcThreads) k_dc(PlanDev P, DcArgs a, int batc
     if (tid == 0 && a.info) {
         a.info[2 * b] = solved ? 1 : 0;
         a.info[2 * b + 1] = c.newton;
+    }
+}
+
+
+// --------------------------------------------------------------------------------------------- //
+// One-warp engine for small circuits (M <= MMAX <= 24 unknowns, at most 32 evaluation lanes): the same analysis
+// with the same arithmetic in the same order, organised for latency instead of generality --
+//  * all vectors (x, xk, xprev, x0) live one element per lane, the limiter states in the registers of the lane
+//    that owns the junction;
+//  * a BJT is evaluated by two lanes (B-E junction / B-C junction: limiter, exponentials, junction currents and
+//    conductances), which exchange their results by shuffle, share Qb and It, and each finish one of gmf / gmr;
+//  * the ordered stamping is done per matrix ENTRY: entry e of [A | z] adds its contributions in netlist order
+//    (plan-time CSR), so the summation order of dc_apply_stamps is kept while the entries run in parallel;
+//  * the linear solve keeps every row in the registers of one lane: pivot search by redux on the bit pattern
+//    (ties: lowest current row position, the idamax rule), the reciprocal of every candidate computed while the
+//    vote is in flight, pivot row broadcast by shuffle, implicit row interchange (a position per lane).
+// --------------------------------------------------------------------------------------------- //
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double dcw_gather(double x, int n) {  // dc_v: node voltage, 0 for ground
+    const double v = shfl_d(x, n > 0 ? n - 1 : 0);
+    return n > 0 ? v : 0.;
+}
+
+template <int MMAX>
+struct DcWarp {
+    // role of this lane
+    int kind, half, t, n1, n2, n3, partner;
+    double st0, st1, st2;  // limiter state (junction voltage of the previous evaluation); diode: It, gt
+    // hoisted constants.  BJT junction lane: lim, nvt1 (Nf|Nr Vt), nvt2 (Ne|Nc Vt), Is, Is2 (Ise|Isc), beta (Bf|Br),
+    // g10 = Is / (N1 Vt beta), g20 = Is2 / (N2 Vt), Vx (Var|Vaf), Ikx (Ikf|Ikr), type; shared: Vaf, Var, Ikf, Ikr
+    double lim, nvt1, nvt2, Is, Is2, beta, g10, g20, Vx, Ikx, type, Vaf, Var, Ikf, Ikr;
+    // diode lane: lim, nvt1 = N Vt, nvt2 = Nr Vt, Is, Is2 = Isr, g10 = Is / (N Vt), g20 = Isr / (Nr Vt),
+    // Ikx = Ikf, Vx = Bv, beta = Ibv, Vaf = Vt, Var = Rs;  cubic lane: Is = alpha
+    int M, N, LD, nnl, lane;
+    double *A, *z, *dout, *Aw;
+    const int *ent_ptr;  // shared-memory copy of DcArgs::ent_tab
+    int newton;
+    unsigned long long tmark;
+
+    __device__ __forceinline__ void eval(double xk) {
+        const double Va = dcw_gather(xk, n1), Vb_ = dcw_gather(xk, n2), Vc_ = dcw_gather(xk, n3);
+        double *o = dout + (size_t)kDcOut * t;
+        const double gmin = 1e-12;
+        // every shuffle below is executed by the whole warp, outside the role branches
+        double Vj = 0., Ij = 0., Ibj = 0., gj = 0., gij = 0.;
+        if (kind == 1) {  // BJT junction lane: n1 = B, n2 = C, n3 = E (BJT.py:319-416)
+            Vj = (Va - (half ? Vb_ : Vc_)) * type;
+            Vj = dc_limit(st0, Vj, lim);
+            const double e1 = exp_lim(Vj / nvt1), e2 = exp_lim(Vj / nvt2);
+            Ij = Is * (e1 - 1.);                       // If | Ir
+            const double Ibi = Ij / beta;
+            const double Ibn = Is2 * (e2 - 1.);
+            Ibj = Ibi + Ibn + gmin * Vj;               // Ibe | Ibc
+            const double gbi = g10 * e1;
+            const double gbn = g20 * e2;
+            gj = gbi + gbn + gmin;                     // gpi | gmu
+            gij = gbi * beta;                          // gif | gir
+        } else if (kind == 0) {  // Diode.calc_dc + add_dc_stamps, Diode.py:98-116, :238-294
+            const double Vt = Vaf, Rs = Var, Ikf_ = Ikx, Bv = Vx, Ibv = beta;
+            const double Vtot = Va - Vb_;
+            double Id = st1 + st2 * Vtot;
+            double Vd = Vtot - Id * Rs;
+            Vd = dc_limit(st0, Vd, lim);
+            const double ef = exp_lim(Vd / nvt1), er = exp_lim(Vd / nvt2);
+            double Idf = Is * (ef - 1.);
+            double gdf = g10 * ef;
+            const double Idr = Is2 * (er - 1.);
+            const double gdr = g20 * er;
+            if (isfinite(Ikf_)) {
+                Idf = Idf * sqrt(Ikf_ / (Ikf_ + Idf));
+                gdf = gdf * (1. - 0.5 * Idf / (Ikf_ + Idf)) * sqrt(Ikf_ / (Ikf_ + Idf));
+            }
+            double Ibr = 0., gbr = 0.;
+            if (isfinite(Bv)) {
+                Ibr = Ibv * exp_lim(-Bv / Vt) * (1. - exp_lim(-Vd / Vt));
+                gbr = Ibv / Vt * exp_lim(-(Bv + Vd) / Vt);
+            }
+            Id = Idf + Idr + Ibr + (Vd * 1e-12);
+            const double gd = gdf + gdr + gbr + (1e-12);
+            st1 = (Id - gd * Vd) / (1. + gd * Rs);
+            st2 = gd / (1. + gd * Rs);
+            o[0] = st2;
+            o[1] = st1;
+        } else if (kind == 2) {  // CubicNonLinearity.add_dc_stamps, CubicNonLinearity.py:20-34
+            const double alpha = Is;
+            const double V = Va - Vb_;
+            const double g = 3 * alpha * V * V;
+            const double I = alpha * V * V * V;
+            o[0] = g;
+            o[1] = I - g * V;
+        }
+        const double Vo = shfl_d(Vj, partner), Io = shfl_d(Ij, partner);
+        double gm = 0., Ieq = 0., It = 0.;
+        const double Vbe = half ? Vo : Vj, Vbc = half ? Vj : Vo;
+        if (kind == 1) {
+            const double If = half ? Io : Ij, Ir = half ? Ij : Io;
+            const double Q1 = 1. / (1. - (Vbc / Vaf) - (Vbe / Var));
+            const double Q2 = (If / Ikf) + (Ir / Ikr);
+            const double sq = sqrt(1. + 4. * Q2);
+            const double Qb = (Q1 / 2.) * (1. + sq);
+            It = (If - Ir) / Qb;
+            const double dQ = Q1 * ((Qb / Vx) + (gij / (Ikx * sq)));  // dQb_dVbe | dQb_dVbc
+            gm = (1. / Qb) * ((half ? -gij : gij) - It * dQ);          // gmf | gmr
+            Ieq = Ibj - gj * Vj;                                       // Ibeeq | Ibceq
+        }
+        const double go = shfl_d(gj, partner), gmo = shfl_d(gm, partner), Ieqo = shfl_d(Ieq, partner);
+        if (kind == 1) {
+            const double gpi = half ? go : gj, gmu = half ? gj : go;
+            const double gmf = half ? gmo : gm, gmr = half ? gm : gmo;
+            const double Ibeeq = half ? Ieqo : Ieq, Ibceq = half ? Ieq : Ieqo;
+            const double Iceeq = It - gmf * Vbe - gmr * Vbc;
+            if (!half) {
+                o[0] = gmu + gpi;
+                o[1] = -gmu;
+                o[2] = -gpi;
+                o[3] = -gmu + gmf + gmr;
+                o[4] = gmu - gmr;
+                o[5] = -gmf;
+            } else {
+                o[6] = -gpi - gmf - gmr;
+                o[7] = gmr;
+                o[8] = gpi + gmf;
+                o[9] = (-Ibeeq - Ibceq) * type;
+                o[10] = (+Ibceq - Iceeq) * type;
+                o[11] = (+Ibeeq + Iceeq) * type;
+            }
+        }
+    }
+
+    // check_vlimit on the new solution (advances the limiter state); this lane's verdict
+    __device__ __forceinline__ bool vlimit(double x, double vabstol) {
+        const double Va = dcw_gather(x, n1), Vb_ = dcw_gather(x, n2), Vc_ = dcw_gather(x, n3);
+        if (kind == 1) {
+            const double Vj = (Va - (half ? Vb_ : Vc_)) * type;
+            const double Vl = dc_limit(st0, Vj, lim);
+            return !(Vj - Vl > vabstol);
+        }
+        if (kind == 0) {
+            const double Vtot = Va - Vb_;
+            const double Id = st1 + st2 * Vtot;
+            const double Vd = Vtot - Id * Var;
+            const double Vl = dc_limit(st0, Vd, lim);
+            return !(Vd - Vl > vabstol);
+        }
+        return true;
+    }
+
+    // [A + extra_g | zscale z] + ordered nonlinear stamps -> Aw (shared), then the solve; returns x (element = lane)
+    __device__ __forceinline__ double assemble_solve(double extra_g, double zscale) {
+        const int NE = M * M + M;
+        const int *ent_dst = ent_ptr + NE + 1, *ent_item = ent_dst + NE;
+        for (int e = lane; e < NE; e += 32) {
+            const int p0 = ent_ptr[e], p1 = ent_ptr[e + 1], dst = ent_dst[e];
+            double base = A[e];  // z follows A
+            if (e < M * M) {
+                if (extra_g != 0. && (dst >> 16)) base = base + extra_g;
+            } else {
+                base = zscale * base;
+            }
+            double acc = 0.;
+            for (int p = p0; p < p1; ++p) {
+                const int it = ent_item[p];
+                const double v = dout[it >> 1];
+                acc = acc + ((it & 1) ? -v : v);
+            }
+            Aw[dst & 0xffff] = base + acc;
+        }
+        __syncwarp();
+        if (lane == 0) YHB_TACC_(25);
+        double a[MMAX], r = 0.;
+#pragma unroll
+        for (int j = 0; j < MMAX; ++j) a[j] = (lane < M && j < M) ? Aw[lane * LD + j] : 0.;
+        if (lane < M) r = Aw[lane * LD + M];
+        __syncwarp();
+        int pos = lane;
+        int piv[MMAX];
+        static_for<0, MMAX>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            piv[k] = 0;
+            if (k < M) {
+                const bool cand = lane < M && pos >= k;
+                // every candidate inverts its own entry while the vote is in flight (the division's fast path: no
+                // branch to the special cases that the structural zeros of the matrix would take; zero pivot -> NaN)
+                const double rc = rcp_fast(cand ? a[k] : 1.);
+                const unsigned long long bits = cand ? (unsigned long long)__double_as_longlong(fabs(a[k])) : 0ull;
+                const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+                const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+                int pp = __reduce_min_sync(0xffffffffu, (cand && hi == mhi && lo == mlo) ? pos : 0x7fffffff);
+                if (pp == 0x7fffffff) pp = k;
+                const int pl = __ffs(__ballot_sync(0xffffffffu, lane < M && pos == pp)) - 1;
+                piv[k] = pl;
+                if (pos == k) pos = pp;  // implicit interchange of positions k and pp
+                if (lane == pl) pos = k;
+                const double rinv = shfl_d(rc, pl);
+                const double l = -(a[k] * rinv);
+                const bool live = lane < M && pos > k;
+#pragma unroll
+                for (int j = k + 1; j < MMAX; ++j) {
+                    const double pj = shfl_d(a[j], pl);
+                    if (live) a[j] = fma(l, pj, a[j]);
+                }
+                const double pr = shfl_d(r, pl);
+                if (live) r = fma(l, pr, r);
+            }
+        });
+        double x = 0.;
+        static_for<0, MMAX>([&](auto jc) {
+            constexpr int j = MMAX - 1 - decltype(jc)::value;
+            if (j < M) {
+                const bool own = lane == piv[j];  // the other lanes divide 1 by 1: no special-case path
+                const double xj = shfl_d((own ? r : 1.) / (own ? a[j] : 1.), piv[j]);
+                if (lane < M && pos < j) r = fma(-a[j], xj, r);
+                if (lane == j) x = xj;
+            }
+        });
+        return x;
+    }
+
+    // DC.solve_dc_nonlinear (DC.py:125-191); x in / out per lane.  Uniform return value.
+    __device__ __forceinline__ bool newton_loop(double extra_g, double zscale, double xstart, double &x) {
+        const double reltol = 1e-3, vabstol = 1e-6, iabstol = 1e-12;
+        const int maxiter = 150;
+        double xk = xstart;
+        int k = 0;
+        bool converged = false;
+        while (!converged && k < maxiter) {
+            YHB_T0_();
+            eval(xk);
+            __syncwarp();
+            if (lane == 0) YHB_TACC_(24);
+            x = assemble_solve(extra_g, zscale);
+            newton += 1;
+            if (lane == 0) YHB_TACC_(27);
+            if (__any_sync(0xffffffffu, lane < M && isnan(x))) return false;  // Solver.py:14
+            bool okc = true;
+            if (lane < M && fabs(x - xk) > reltol * fabs(xk) + (lane < N ? vabstol : iabstol)) okc = false;
+            const bool vl = vlimit(x, vabstol);
+            converged = __all_sync(0xffffffffu, okc && vl);
+            if (!converged) {
+                xk = x;
+                k = k + 1;
+            }
+            if (lane == 0) YHB_TACC_(28);
+        }
+        return converged;
+    }
+};
+
+template <int MMAX>
+__global__ void __launch_bounds__(32) k_dc_warp(PlanDev P, DcArgs a, int batch) {
+    extern __shared__ double smw[];
+    const int b = blockIdx.x;
+    if (b >= batch) return;
+    const int M = a.M, N = P.N, lane = threadIdx.x;
+    DcWarp<MMAX> w;
+    w.M = M;
+    w.N = N;
+    w.LD = (M + 1) | 1;
+    w.nnl = a.nnl;
+    w.lane = lane;
+    w.A = smw;
+    w.z = w.A + M * M;
+    w.dout = w.z + M;
+    w.Aw = w.dout + (size_t)kDcOut * max(a.nnl, 1);
+    int *tab = reinterpret_cast<int *>(w.Aw + (size_t)M * w.LD);
+    for (int i = lane; i < a.ent_ints; i += 32) tab[i] = a.ent_tab[i];
+    w.ent_ptr = tab;
+    w.newton = 0;
+    // role of this lane; hoisted constants with the operations of calc_dc
+    const int *lt = a.lane_tab + kDcLaneInts * lane;
+    w.kind = lt[0]; w.half = lt[1]; w.t = lt[2];
+    const int idx = lt[3];
+    w.n1 = lt[4]; w.n2 = lt[5]; w.n3 = lt[6]; w.partner = lt[7];
+    w.st0 = w.st1 = w.st2 = 0.;  // Diode.init / BJT.init
+    w.lim = w.nvt1 = w.nvt2 = w.Is = w.Is2 = w.beta = w.g10 = w.g20 = w.Vx = w.Ikx = w.type = 1.;
+    w.Vaf = w.Var = w.Ikf = w.Ikr = 1.;
+    if (w.kind == 1) {
+        const double *p = a.bjt_par + ((size_t)b * P.nb + idx) * YHB_BJT_NPAR;
+        const double A_ = p[YHB_BJT_AREA];
+        const double Vt = YHB_K_BOLTZ * p[YHB_BJT_TEMP] / YHB_Q_ELEM;
+        const double N1 = w.half ? p[YHB_BJT_NR] : p[YHB_BJT_NF], N2 = w.half ? p[YHB_BJT_NC] : p[YHB_BJT_NE];
+        w.type = p[YHB_BJT_TYPE];
+        w.Is = p[YHB_BJT_IS] * A_;
+        w.Is2 = (w.half ? p[YHB_BJT_ISC] : p[YHB_BJT_ISE]) * A_;
+        w.beta = w.half ? p[YHB_BJT_BR] : p[YHB_BJT_BF];
+        w.Ikf = p[YHB_BJT_IKF] * A_;
+        w.Ikr = p[YHB_BJT_IKR] * A_;
+        w.Vaf = p[YHB_BJT_VAF];
+        w.Var = p[YHB_BJT_VAR];
+        w.Vx = w.half ? w.Vaf : w.Var;
+        w.Ikx = w.half ? w.Ikr : w.Ikf;
+        w.lim = 10. * N1 * Vt;
+        w.nvt1 = N1 * Vt;
+        w.nvt2 = N2 * Vt;
+        w.g10 = w.Is / (N1 * Vt * w.beta);
+        w.g20 = w.Is2 / (N2 * Vt);
+    } else if (w.kind == 0) {
+        const double *p = a.diode_par + ((size_t)b * P.nd + idx) * YHB_DIODE_NPAR;
+        const double A_ = p[YHB_DIODE_AREA];
+        const double Vt = YHB_K_BOLTZ * p[YHB_DIODE_TEMP] / YHB_Q_ELEM;
+        const double Nn = p[YHB_DIODE_N], Nr = p[YHB_DIODE_NR];
+        w.Is = p[YHB_DIODE_IS] * A_;
+        w.Is2 = p[YHB_DIODE_ISR] * A_;
+        w.Ikx = p[YHB_DIODE_IKF] * A_;
+        w.beta = p[YHB_DIODE_IBV] * A_;
+        w.Var = p[YHB_DIODE_RS] / A_;
+        w.Vx = p[YHB_DIODE_BV];
+        w.Vaf = Vt;
+        w.lim = 10. * Nn * Vt;
+        w.nvt1 = Nn * Vt;
+        w.nvt2 = Nr * Vt;
+        w.g10 = w.Is / (Nn * Vt);
+        w.g20 = w.Is2 / (Nr * Vt);
+    } else if (w.kind == 2) {
+        w.Is = a.cubic_par[(size_t)b * P.nc + idx];
+    }
+
+    for (int i = lane; i < M * M + M; i += 32) w.A[i] = 0.;  // A and z are contiguous
+    __syncwarp();
+    if (lane == 0) dc_stamp_linear(P, a, b, w.A, w.z, M);
+    __syncwarp();
+
+    double x = 0., x0 = 0., xprev = 0.;
+    bool solved = false;
+    if (a.nnl == 0) {  // DC.py:90-95
+        x = w.assemble_solve(0., 1.);
+        solved = !__any_sync(0xffffffffu, lane < M && isnan(x));
+    }
+    // DC.run: plain Newton, then source stepping (DC.py:236-279), then gmin stepping (DC.py:193-234); one call
+    // site of the Newton loop, driven by a small state machine
+    int phase = solved ? 3 : 0, k = 0;
+    double alpha = 1e-3, delta = 1e-3, gmin = 0.01, rate = 0.05;
+    while (phase < 3) {
+        const double eg = phase == 2 ? gmin : 0.;
+        const double zs = phase == 1 ? alpha : 1.;
+        if (phase != 0) x0 = x;
+        const bool ok = w.newton_loop(eg, zs, x0, x);
+        if (phase == 0) {
+            if (ok) { solved = true; phase = 3; }
+            else { phase = 1; xprev = x0; x = x0; k = 0; }
+        } else if (phase == 1) {
+            bool stop = false;
+            if (ok) {
+                xprev = x;
+                if (alpha >= 1.0) { solved = true; phase = 3; }
+                else {
+                    alpha = alpha + delta;
+                    delta = 2 * delta;
+                    if (alpha >= 1.0) alpha = 1.0;
+                }
+            } else {
+                x = xprev;
+                alpha = alpha - delta / 2;
+                delta = delta / 2;
+                if (alpha < 1e-3) stop = true;
+            }
+            k = k + 1;
+            if (phase == 1 && (stop || k >= 50)) { phase = 2; xprev = 0.; x = 0.; k = 0; }
+        } else {
+            if (ok) {
+                xprev = x;
+                if (gmin < 1e-12) { solved = true; phase = 3; }
+                else {
+                    gmin = gmin * rate;
+                    rate = rate / 4;
+                }
+            } else {
+                x = xprev;
+                gmin = gmin / rate;
+                rate = 2 * rate;
+                if (gmin > 0.01) phase = 3;
+            }
+            k = k + 1;
+            if (k >= 10000) phase = 3;
+        }
+    }
+    if (lane < N) a.Vdc[(size_t)b * N + lane] = x;
+    if (lane == 0 && a.info) {
+        a.info[2 * b] = solved ? 1 : 0;
+        a.info[2 * b + 1] = w.newton;
     }
 }
 
