@@ -105,12 +105,14 @@ def get_plan(netlist, freq, numharmonics, flags=0, match_tones=True):
     return plan, topo
 
 
-def _host_array(shape, dtype, pinned):
-    """zeroed host array; page-locked (through torch) when a GPU is present so that D2H copies run at full speed"""
+def _host_array(shape, dtype, pinned, zero=True):
+    """host array; page-locked (through torch's caching host allocator) when a GPU is present so that H2D / D2H
+    copies run at full speed.  zero=False: the caller overwrites every element (results of a D2H copy)."""
     if pinned:
         import torch
         tdt = {np.float64: torch.float64, np.int32: torch.int32, np.complex128: torch.complex128}[dtype]
-        return torch.zeros(shape, dtype=tdt, pin_memory=True).numpy()
+        make = torch.zeros if zero else torch.empty
+        return make(shape, dtype=tdt, pin_memory=True).numpy()
     return np.zeros(shape, dtype=dtype)
 
 
@@ -119,14 +121,15 @@ class BatchResult:
 
     def __init__(self, plan, B, pinned=False):
         self.B = B
-        self.V = _host_array((B, plan.W), np.float64, pinned)
-        self.Vf = _host_array((B, plan.N, plan.K + 1), np.complex128, pinned)
-        self.converged = _host_array((B,), np.int32, pinned)
-        self.newton_iters = _host_array((B,), np.int32, pinned)
-        self.lu_count = _host_array((B,), np.int32, pinned)
-        self.level_iters = _host_array((B, L.MAX_LEVELS), np.int32, pinned)
-        self.level_alpha = _host_array((B, L.MAX_LEVELS), np.float64, pinned)
-        self.err = _host_array((B,), np.float64, pinned)
+        # every array is written in full by the D2H copies of yhb_run_host / the gather of _dist: no zero fill
+        self.V = _host_array((B, plan.W), np.float64, pinned, zero=False)
+        self.Vf = _host_array((B, plan.N, plan.K + 1), np.complex128, pinned, zero=False)
+        self.converged = _host_array((B,), np.int32, pinned, zero=False)
+        self.newton_iters = _host_array((B,), np.int32, pinned, zero=False)
+        self.lu_count = _host_array((B,), np.int32, pinned, zero=False)
+        self.level_iters = _host_array((B, L.MAX_LEVELS), np.int32, pinned, zero=False)
+        self.level_alpha = _host_array((B, L.MAX_LEVELS), np.float64, pinned, zero=False)
+        self.err = _host_array((B,), np.float64, pinned, zero=False)
 
     def levels(self, b=0):
         it = self.level_iters[b]

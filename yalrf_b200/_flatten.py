@@ -66,15 +66,33 @@ def source_kinds(topo, freq, match_tones=True):
     return kinds
 
 
+def _zeros(shape, pinned):
+    """zeroed float64 host array; page-locked for large batches on a GPU box so that the H2D copies of
+    yhb_run_host are asynchronous DMA transfers instead of staged pageable copies"""
+    if pinned:
+        import torch
+        return torch.zeros(shape, dtype=torch.float64, pin_memory=True).numpy()
+    return np.zeros(shape)
+
+
+def _want_pinned(B):
+    if B < 256:
+        return False
+    import torch
+    return torch.cuda.is_available()
+
+
 class ParamBlock:
     """Parameter arrays of a batch of B circuits sharing one topology."""
 
     def __init__(self, topo, freq, B=1):
         self.topo = topo
         self.B = B
+        pinned = _want_pinned(B)
         f = (freq, 0.0) if topo.num_tones == 1 else (freq[0], freq[1])
-        self.tones = np.tile(np.array(f, dtype=np.float64), (B, 1))
-        self.lin_val = np.zeros((B, max(len(topo.lin), 1), 2))
+        self.tones = _zeros((B, 2), pinned)
+        self.tones[:] = np.array(f, dtype=np.float64)
+        self.lin_val = _zeros((B, max(len(topo.lin), 1), 2), pinned)
         for i, (kind, _, dev) in enumerate(topo.lin):
             if kind == L.LIN_RESISTOR:
                 self.lin_val[:, i, 0] = dev.R
@@ -87,21 +105,21 @@ class ParamBlock:
             else:
                 self.lin_val[:, i, 0] = dev.freq
                 self.lin_val[:, i, 1] = dev.g
-        self.src_val = np.zeros((B, max(len(topo.src), 1), 3))
+        self.src_val = _zeros((B, max(len(topo.src), 1), 3), pinned)
         self.src_ac = np.zeros((B, max(len(topo.src), 1)))
         self.src_phase = np.zeros((B, max(len(topo.src), 1)))
         for i, (_, dev) in enumerate(topo.src):
             self.src_val[:, i, 0] = dev.dc
             self.src_ac[:, i] = dev.ac
             self.src_phase[:, i] = dev.phase
-        self.diode_par = np.zeros((B, max(len(topo.diodes), 1), L.DIODE_NPAR))
+        self.diode_par = _zeros((B, max(len(topo.diodes), 1), L.DIODE_NPAR), pinned)
         for i, (_, dev) in enumerate(topo.diodes):
             self.diode_par[:, i, :] = [float(dev.options[k]) for k in L.DIODE_PARAMS]
-        self.bjt_par = np.zeros((B, max(len(topo.bjts), 1), L.BJT_NPAR))
+        self.bjt_par = _zeros((B, max(len(topo.bjts), 1), L.BJT_NPAR), pinned)
         for i, (_, dev) in enumerate(topo.bjts):
             self.bjt_par[:, i, :-1] = [float(dev.options[k]) for k in L.BJT_PARAMS[:-1]]
             self.bjt_par[:, i, -1] = float(dev.type)
-        self.cubic_par = np.zeros((B, max(len(topo.cubics), 1)))
+        self.cubic_par = _zeros((B, max(len(topo.cubics), 1)), pinned)
         for i, (_, dev) in enumerate(topo.cubics):
             self.cubic_par[:, i] = dev.alpha
 

@@ -39,7 +39,7 @@ struct FusedChoice {
     bool ok;
     int NT;       // 8 x 8 tiles per dimension of the core system (0 = scalar elimination in shared memory)
     size_t smem;  // dynamic shared memory bytes
-    int hot;      // plan tables staged in shared memory
+    int hot;      // bit 0: plan tables staged in shared memory; bit 1: per-circuit ylin / omega cached in shared memory
 };
 
 constexpr size_t kMaxEvalSmem = 200 * 1024;
@@ -50,6 +50,13 @@ constexpr size_t kMaxEvalSmem = 200 * 1024;
 // which fused-engine variant runs this plan (if any)
 static FusedChoice fused_choice(const PlanDev &d) {
     constexpr size_t lim = 227 * 1024 - 2048;  // dynamic part: the 227 KB per-CTA limit includes the static __shared__
+    constexpr size_t lim2 = 113 * 1024 - 1024;  // ... of a CTA that shares the SM with a second one
+    // the linear cache is appended when it does not cost residency (2 CTAs/SM stay 2) and fits
+    auto with_cache = [&](size_t b, int hot) {
+        const size_t c = (fused_lin_cache_doubles(d) + 2) * sizeof(double);
+        const bool fits = b <= lim2 ? b + c <= lim2 : b + c <= lim;
+        return fits ? FusedChoice{true, 0, b + c, hot | 2} : FusedChoice{true, 0, b, hot};
+    };
     FusedChoice f{false, 0, 0, 0};
     if (d.flags & YHB_FLAG_STAGED) return f;
     const int need = std::max(1, (d.Wc + 1 + 7) / 8);
@@ -57,12 +64,12 @@ static FusedChoice fused_choice(const PlanDev &d) {
 #define YHB_CASE(t)                                                                 \
     if (need <= t) {                                                                \
         size_t b = fused_smem_doubles<t>(d, hot != 0) * sizeof(double);             \
-        if (b <= lim) return FusedChoice{true, t, b, hot};                          \
+        if (b <= lim) { FusedChoice c = with_cache(b, hot); c.NT = t; return c; }   \
     }
         YHB_FOR_NT(YHB_CASE)
 #undef YHB_CASE
         size_t b = fused_smem_doubles<0>(d, hot != 0) * sizeof(double);
-        if (b <= lim) return FusedChoice{true, 0, b, hot};
+        if (b <= lim) return with_cache(b, hot);
     }
     return f;
 }
