@@ -89,39 +89,52 @@ class ParamBlock:
         self.topo = topo
         self.B = B
         pinned = _want_pinned(B)
+        # one template row per array (the netlist's current values, re-read at every run), broadcast over the batch
+        # with a single contiguous copy each
         f = (freq, 0.0) if topo.num_tones == 1 else (freq[0], freq[1])
-        self.tones = _zeros((B, 2), pinned)
-        self.tones[:] = np.array(f, dtype=np.float64)
-        self.lin_val = _zeros((B, max(len(topo.lin), 1), 2), pinned)
+        lin = np.zeros((max(len(topo.lin), 1), 2))
         for i, (kind, _, dev) in enumerate(topo.lin):
             if kind == L.LIN_RESISTOR:
-                self.lin_val[:, i, 0] = dev.R
+                lin[i, 0] = dev.R
             elif kind == L.LIN_CAPACITOR:
-                self.lin_val[:, i, 0] = dev.C
+                lin[i, 0] = dev.C
             elif kind == L.LIN_INDUCTOR:
-                self.lin_val[:, i, 0] = dev.L
+                lin[i, 0] = dev.L
             elif kind == L.LIN_GYRATOR:
-                self.lin_val[:, i, 0] = dev.G
+                lin[i, 0] = dev.G
             else:
-                self.lin_val[:, i, 0] = dev.freq
-                self.lin_val[:, i, 1] = dev.g
-        self.src_val = _zeros((B, max(len(topo.src), 1), 3), pinned)
-        self.src_ac = np.zeros((B, max(len(topo.src), 1)))
-        self.src_phase = np.zeros((B, max(len(topo.src), 1)))
+                lin[i, 0] = dev.freq
+                lin[i, 1] = dev.g
+        nsrc = max(len(topo.src), 1)
+        src, ac, ph = np.zeros((nsrc, 3)), np.zeros(nsrc), np.zeros(nsrc)
         for i, (_, dev) in enumerate(topo.src):
-            self.src_val[:, i, 0] = dev.dc
-            self.src_ac[:, i] = dev.ac
-            self.src_phase[:, i] = dev.phase
-        self.diode_par = _zeros((B, max(len(topo.diodes), 1), L.DIODE_NPAR), pinned)
+            src[i, 0] = dev.dc
+            ac[i] = dev.ac
+            ph[i] = dev.phase
+        dio = np.zeros((max(len(topo.diodes), 1), L.DIODE_NPAR))
         for i, (_, dev) in enumerate(topo.diodes):
-            self.diode_par[:, i, :] = [float(dev.options[k]) for k in L.DIODE_PARAMS]
-        self.bjt_par = _zeros((B, max(len(topo.bjts), 1), L.BJT_NPAR), pinned)
+            dio[i, :] = [float(dev.options[k]) for k in L.DIODE_PARAMS]
+        bjt = np.zeros((max(len(topo.bjts), 1), L.BJT_NPAR))
         for i, (_, dev) in enumerate(topo.bjts):
-            self.bjt_par[:, i, :-1] = [float(dev.options[k]) for k in L.BJT_PARAMS[:-1]]
-            self.bjt_par[:, i, -1] = float(dev.type)
-        self.cubic_par = _zeros((B, max(len(topo.cubics), 1)), pinned)
+            bjt[i, :-1] = [float(dev.options[k]) for k in L.BJT_PARAMS[:-1]]
+            bjt[i, -1] = float(dev.type)
+        cub = np.zeros(max(len(topo.cubics), 1))
         for i, (_, dev) in enumerate(topo.cubics):
-            self.cubic_par[:, i] = dev.alpha
+            cub[i] = dev.alpha
+
+        def batch(row):
+            out = _zeros((B,) + row.shape, pinned)
+            out[:] = row
+            return out
+
+        self.tones = batch(np.array(f, dtype=np.float64))
+        self.lin_val = batch(lin)
+        self.src_val = batch(src)
+        self.src_ac = np.tile(ac, (B, 1))
+        self.src_phase = np.tile(ph, (B, 1))
+        self.diode_par = batch(dio)
+        self.bjt_par = batch(bjt)
+        self.cubic_par = batch(cub)
 
     # ---- sweeps: override one field of one device for the whole batch
     def set(self, dev, field, values):
