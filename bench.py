@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 
 GRID = 64
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused launch over the 4096-point grid (ncu --set full, profiles/)
-FUSED_TRAFFIC_BYTES = {'diffamp': 46917120, 'activeload': None}
+FUSED_TRAFFIC_BYTES = {'diffamp': 48572160, 'activeload': None}
 
 
 def grid_points(rank, world, workload):
@@ -287,7 +287,7 @@ def run_gpu(args):
                                  'trailing updates on the FP64 tensor pipe).  peak = DFMA microbenchmark run live '
                                  '(MEASURED_PEAKS.json has no fp64 figure; DMMA m8n8k4 measured at 36.8 TFLOP/s, '
                                  'profiles/r01_microbench.txt).  ncu (profiles/r01_bench_fused_full.txt): DMMA pipe '
-                                 'active 8.8 %%, FP64 pipe 5.1 %%, issue slots 28 %%: the kernel is bound by the serial '
+                                 'active 9.1 %%, FP64 pipe 5.3 %%, issue slots 29 %%: the kernel is bound by the serial '
                                  'pivot chain at 2 resident circuits per SM.  traffic = dram bytes of one launch from '
                                  'ncu --set full.' % (W, wc)})
         else:
