@@ -74,6 +74,8 @@ enum {
                                      for large blocks (config 5: ladders at many harmonics), where the one-CTA banded
                                      elimination is out of reach */
 #define YHB_FLAG_NO_BLOCK_THOMAS 64
+#define YHB_FLAG_NO_BLOCK_SPARSE 128 /* fused engine: dense Gauss-Jordan of the core even when its node blocks are sparse */
+#define YHB_FLAG_BLOCK_SPARSE 256    /* fused engine: block-sparse LU of the core whenever it applies (also for dense block structures) */
 
 #define YHB_MAX_LEVELS 64 /* hb_loop calls recorded per solve: 1 direct attempt + <=50 continuation levels */
 
@@ -175,6 +177,10 @@ int yhb_plan_core(const yhb_plan *plan, int32_t *Nc, int32_t *Wc, int32_t *fused
 int yhb_plan_band(const yhb_plan *plan);
 /* which engine yhb_solve runs for this plan: 0 fused (on chip), 1 staged dense, 2 staged banded, 3 staged block-Thomas */
 int yhb_plan_engine(const yhb_plan *plan);
+/* fused engine: number of levels of the block-sparse LU over node blocks the plan will run (the nodes of a level are
+ * factored concurrently), 0 = dense Gauss-Jordan of the whole core; *doubles (optional) = size of the block-row
+ * storage in doubles */
+int yhb_plan_block_sparse(const yhb_plan *plan, int32_t *doubles);
 /* real frequency of each bin of circuit tones (f1, f2), as self.freqs (:251, :271): host helper */
 int yhb_plan_freqs(const yhb_plan *plan, double f1, double f2, double *freqs /* [K+1] */);
 

@@ -394,6 +394,55 @@ def test_vanderpol_newton(yb, golden):
     assert abs(r.fosc[1] - r.fosc[0]) / r.fosc[0] < 1e-9
 
 
+# ----------------------------------------------------------------------------- fused engine: block-sparse core LU
+@pytest.mark.parametrize('mode', [None, True, False])
+def test_block_sparse_core_lu(yb, golden, mode):
+    """The fused engine factors the core node block by node block when its block structure is sparse (DiffAmp: the
+    collectors and the mirror node couple to the emitter node only, 2 levels), hb.block_sparse = True forces it on
+    dense block structures too, False keeps the dense Gauss-Jordan: all three reproduce the reference."""
+    g = golden('diffamp_cold_grid')
+    y = yb.YalRF('Differential Amplifier')
+    h = circuits.diffamp(y)
+    vb, vin = np.meshgrid(g['vbs'], g['vins'], indexing='ij')
+    vb, vin = vb.ravel(), vin.ravel()
+    hb = mthb('HB1', h['freq'], h['K'])
+    hb.block_sparse = mode
+    res = hb.run_sweep(y, [(h['i2'], 'ac', vin / 2), (h['i4'], 'ac', vin / 2), (h['i3'], 'dc', vb), (h['i5'], 'dc', vb)])
+    assert hb._plan.engine() == 'fused'
+    assert hb._plan.block_sparse() == (0 if mode is False else 2)
+    for k in range(len(vb)):
+        its = g['iters'][k]
+        assert bool(res.converged[k]) == bool(g['converged'][k])
+        assert res.levels(k) == its[its > 0].tolist(), (k, mode)
+        assert relmax(res.V[k], g['V'][k][:, 0]) < 1e-9, (k, mode)
+
+    # warm-start chain of tests/HB_DiffAmp.py
+    g = golden('diffamp_warm_sweep')
+    V0 = None
+    for k, v in enumerate(g['vins'][:8]):
+        h['i2'].ac = v / 2
+        h['i4'].ac = v / 2
+        conv, freqs, Vf, _, _ = hb.run(y, V0)
+        V0 = hb.V
+        its = g['iters'][k]
+        assert conv and hb.last.levels() == its[its > 0].tolist()
+        assert relmax(hb.V, g['V'][k]) < 1e-9
+
+    # dense block structures (forced) and single-node cores (never): Peltz with the probe fixed, current mirror, hb_bjt
+    for tag, builder in [('current_mirror', 'current_mirror'), ('hb_bjt', 'hb_bjt')]:
+        g = golden(tag)
+        y = yb.YalRF(tag)
+        h = getattr(circuits, builder)(y)
+        hb = mthb('HB1', h['freq'], h['K'])
+        hb.block_sparse = mode
+        conv, freqs, Vf, _, _ = hb.run(y)
+        if mode is False:
+            assert hb._plan.block_sparse() == 0
+        assert conv == bool(g['converged'])
+        assert hb.last.levels() == g['iters'].tolist(), (tag, mode)
+        assert relmax(hb.V, g['V']) < 1e-9, (tag, mode)
+
+
 # ----------------------------------------------------------------------------- more reference scripts
 @pytest.mark.parametrize('tag,builder,nh', [('current_mirror', 'current_mirror', None),
                                             ('fullwave_rectifier', 'fullwave_rectifier', None),

@@ -34,6 +34,8 @@ class MultiToneHarmonicBalance:
         self.band = True              # staged engine: band storage for block-banded cores (chains of nodes)
         self.block_thomas = None      # staged engine, block-tridiagonal cores: None = block-by-block solve for large
                                       # blocks (S >= 128), True / False = always / never
+        self.block_sparse = None      # fused engine: None = block-sparse LU over node blocks when the core's block
+                                      # structure is sparse, True / False = whenever it applies / never (dense solve)
         self.distributed = False      # run_batch / run_sweep: shard the circuits over torch.distributed ranks, gather
         self.last = None              # BatchResult of the last call
 
@@ -43,7 +45,9 @@ class MultiToneHarmonicBalance:
                 (0 if self.peel else L.FLAG_NO_PEEL) | (L.FLAG_STAGED if self.engine == 'staged' else 0) |
                 (0 if self.band else L.FLAG_NO_BAND) |
                 (L.FLAG_BLOCK_THOMAS if self.block_thomas else 0) |
-                (L.FLAG_NO_BLOCK_THOMAS if self.block_thomas is False else 0))
+                (L.FLAG_NO_BLOCK_THOMAS if self.block_thomas is False else 0) |
+                (L.FLAG_BLOCK_SPARSE if self.block_sparse else 0) |
+                (L.FLAG_NO_BLOCK_SPARSE if self.block_sparse is False else 0))
 
     def _setup(self, netlist):
         self.netlist = netlist.copy()

@@ -72,6 +72,10 @@ class Plan:
         """'fused' | 'staged-dense' | 'staged-banded' | 'staged-block-thomas': the engine yhb_solve runs for this plan"""
         return L.ENGINES[int(L.lib().yhb_plan_engine(self.handle))]
 
+    def block_sparse(self):
+        """levels of the fused engine's block-sparse LU over node blocks (0 = dense Gauss-Jordan of the core)"""
+        return int(L.lib().yhb_plan_block_sparse(self.handle, None))
+
     def freqs(self, f1, f2=0.0):
         out = np.zeros(self.K + 1)
         L.check(L.lib().yhb_plan_freqs(self.handle, float(f1), float(f2), out.ctypes.data_as(C.POINTER(C.c_double))))

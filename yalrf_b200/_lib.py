@@ -23,6 +23,8 @@ FLAG_STAGED = 8
 FLAG_NO_BAND = 16
 FLAG_BLOCK_THOMAS = 32
 FLAG_NO_BLOCK_THOMAS = 64
+FLAG_NO_BLOCK_SPARSE = 128
+FLAG_BLOCK_SPARSE = 256
 ENGINES = ['fused', 'staged-dense', 'staged-banded', 'staged-block-thomas']
 MAX_LEVELS = 64
 
@@ -62,7 +64,7 @@ PROF_KINDS = ['prepare', 'dc', 'init', 'eval', 'assemble', 'lu', 'finish', 'fuse
 
 EXPORTS = ['yhb_last_error', 'yhb_version', 'yhb_set_device', 'yhb_profile_enable', 'yhb_profile_reset',
            'yhb_profile_read', 'yhb_fp64_peak', 'yhb_plan_create', 'yhb_plan_destroy',
-           'yhb_plan_dims', 'yhb_plan_core', 'yhb_plan_band', 'yhb_plan_engine', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_newton',
+           'yhb_plan_dims', 'yhb_plan_core', 'yhb_plan_band', 'yhb_plan_engine', 'yhb_plan_block_sparse', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_newton',
            'yhb_run_host', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu', 'yhb_stage_gj', 'yhb_debug_timing']
 
 
@@ -88,6 +90,7 @@ def lib():
     L.yhb_plan_core.argtypes = [C.c_void_p, _i32p, _i32p, _i32p]
     L.yhb_plan_band.argtypes = [C.c_void_p]
     L.yhb_plan_engine.argtypes = [C.c_void_p]
+    L.yhb_plan_block_sparse.argtypes = [C.c_void_p, _i32p]
     L.yhb_plan_freqs.argtypes = [C.c_void_p, C.c_double, C.c_double, _f64p]
     L.yhb_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
     L.yhb_workspace_bytes.restype = C.c_size_t

@@ -524,6 +524,109 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
         d.btd = (bwn <= 1 && d.Nc >= 3 && !(desc->flags & YHB_FLAG_NO_BLOCK_THOMAS) &&
                  ((desc->flags & YHB_FLAG_BLOCK_THOMAS) || S >= 128)) ? 1 : 0;
     }
+    // ---- block-sparse LU structure of the core (PlanDev::bs_*): ordering by levels of independent minimum-degree
+    // nodes, fill, block-row storage map
+    std::vector<int> bs_order, bs_pos, bs_level_ptr(1, 0), bs_rowbase, bs_ld, bs_nlater, bs_nblk, bs_rhsoff, bs_coloff,
+        bs_blkof;
+    d.bs_ok = 0;
+    d.bs_nlev = 0;
+    d.bs_total = 0;
+    {
+        const int Nc = d.Nc;
+        bool same = Nc >= 2 && Nc <= 16 && S <= 32 && !(desc->flags & YHB_FLAG_NO_BLOCK_SPARSE);
+        for (int r = 0; same && r < Nc; ++r) same = core_rows[r] == core_cols[r];
+        if (same) {
+            std::vector<std::vector<char>> nz(Nc, std::vector<char>(Nc, 0));
+            for (int r = 0; r < Nc; ++r) {
+                nz[r][r] = 1;
+                for (int p : row_cols[core_rows[r]]) {
+                    int cpos = core_col_of[pairs[p].second];
+                    if (cpos >= 0) nz[r][cpos] = 1;
+                }
+            }
+            int nnz0 = 0;
+            for (int r = 0; r < Nc; ++r)
+                for (int c = 0; c < Nc; ++c) nnz0 += nz[r][c];
+            std::vector<char> gone(Nc, 0);
+            bs_pos.assign(Nc, -1);
+            while ((int)bs_order.size() < Nc) {
+                std::vector<int> deg(Nc, 0);
+                int mind = 1 << 30;
+                for (int k = 0; k < Nc; ++k) {
+                    if (gone[k]) continue;
+                    for (int j = 0; j < Nc; ++j)
+                        if (j != k && !gone[j] && (nz[k][j] || nz[j][k])) deg[k]++;
+                    mind = std::min(mind, deg[k]);
+                }
+                std::vector<int> cand;
+                for (int k = 0; k < Nc; ++k)
+                    if (!gone[k] && deg[k] <= mind + 1) cand.push_back(k);
+                std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return deg[a] < deg[b]; });
+                std::vector<int> level;
+                for (int k : cand) {
+                    bool indep = true;
+                    for (int t : level) indep = indep && !nz[k][t] && !nz[t][k];
+                    if (indep) level.push_back(k);
+                }
+                for (int k : level) {
+                    bs_pos[k] = (int)bs_order.size();
+                    bs_order.push_back(k);
+                    gone[k] = 1;
+                }
+                for (int k : level)  // fill among the remaining neighbours of k
+                    for (int i = 0; i < Nc; ++i)
+                        if (!gone[i] && nz[i][k])
+                            for (int j = 0; j < Nc; ++j)
+                                if (!gone[j] && nz[k][j]) nz[i][j] = 1;
+                bs_level_ptr.push_back((int)bs_order.size());
+            }
+            int nnz1 = 0;
+            for (int r = 0; r < Nc; ++r)
+                for (int c = 0; c < Nc; ++c) nnz1 += nz[r][c];
+            bs_rowbase.assign(Nc, 0);
+            bs_ld.assign(Nc, 0);
+            bs_nlater.assign(Nc, 0);
+            bs_nblk.assign(Nc, 0);
+            bs_rhsoff.assign(Nc, 0);
+            bs_coloff.assign((size_t)Nc * Nc, -1);
+            bs_blkof.assign((size_t)Nc * Nc, -1);
+            size_t total = 0;
+            for (int k = 0; k < Nc; ++k) {
+                std::vector<int> later, earlier;
+                for (int j = 0; j < Nc; ++j) {
+                    if (j == k || !nz[k][j]) continue;
+                    (bs_pos[j] > bs_pos[k] ? later : earlier).push_back(j);
+                }
+                int slot = 0, col = 0;
+                auto put = [&](int j) {
+                    bs_coloff[(size_t)k * Nc + j] = col;
+                    bs_blkof[(size_t)k * Nc + slot] = j;
+                    ++slot;
+                    col += S;
+                };
+                put(k);
+                for (int j : later) put(j);
+                bs_rhsoff[k] = col;
+                col += 1;
+                for (int j : earlier) put(j);
+                bs_nlater[k] = (int)later.size();
+                bs_nblk[k] = slot;
+                bs_ld[k] = col | 1;
+                bs_rowbase[k] = (int)total;
+                total += (size_t)S * bs_ld[k];
+            }
+            const bool sparse = nnz1 < Nc * Nc;
+            // never more than the dense matrix of the fused engine; the pivot permutations ([Nc][32] ints) take the
+            // place of the pair spectra during the solve
+            const bool fits = total <= (size_t)(d.Wc + 1) * (d.Wc + 1) && (size_t)Nc * 16 <= (size_t)d.npair_nl * 2 * S;
+            if (fits && (sparse || (desc->flags & YHB_FLAG_BLOCK_SPARSE))) {
+                d.bs_ok = 1;
+                d.bs_nlev = (int)bs_level_ptr.size() - 1;
+                d.bs_total = (int)total;
+            }
+            (void)nnz0;
+        }
+    }
     d.nA = (int)a_row.size();
     d.nB = (int)b_row.size();
     std::vector<int> a_ptr(1, 0), a_pair, a_m, b_ptr(1, 0), b_pair, b_m, r_ptr(1, 0), r_pair, r_m;
@@ -608,6 +711,9 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     UP(a_row, a_row); UP(a_col, a_col); UP(a_sgn, a_sgn); UP(a_ptr, a_ptr); UP(a_pair, a_pair); UP(a_m, a_m);
     UP(b_row, b_row); UP(b_col, b_col); UP(b_sgn, b_sgn); UP(b_ptr, b_ptr); UP(b_pair, b_pair); UP(b_m, b_m);
     UP(r_ptr, r_ptr); UP(r_pair, r_pair); UP(r_m, r_m);
+    UP(bs_order, bs_order); UP(bs_pos, bs_pos); UP(bs_level_ptr, bs_level_ptr); UP(bs_rowbase, bs_rowbase);
+    UP(bs_ld, bs_ld); UP(bs_nlater, bs_nlater); UP(bs_nblk, bs_nblk); UP(bs_rhsoff, bs_rhsoff);
+    UP(bs_coloff, bs_coloff); UP(bs_blkof, bs_blkof);
     d.blob_hot_bytes = (int)align_up(blob.size(), 16);
     // k_prepare / k_dc only
     UP(bin_k1, pl->bin_k1);
@@ -683,6 +789,13 @@ extern "C" int yhb_plan_engine(const yhb_plan *pl) {
     if (fused_choice(pl->d).ok) return 0;
     if (pl->d.btd) return 3;
     return pl->d.band > 0 ? 2 : 1;
+}
+
+extern "C" int yhb_plan_block_sparse(const yhb_plan *pl, int32_t *doubles) {
+    if (!pl) { set_error("null plan"); return -1; }
+    const bool on = pl->d.bs_ok && fused_choice(pl->d).ok;
+    if (doubles) *doubles = on ? pl->d.bs_total : 0;
+    return on ? pl->d.bs_nlev : 0;
 }
 
 extern "C" int yhb_plan_core(const yhb_plan *pl, int32_t *Nc, int32_t *Wc, int32_t *fused) {

@@ -76,6 +76,21 @@ struct PlanDev {
     const int *b_row, *b_col, *b_sgn;  // [nB]
     const int *b_ptr, *b_pair, *b_m;
     const int *r_ptr, *r_pair, *r_m;   // per core row: entries in A-known columns, CSR [Nc+1]
+    // ---- block-sparse LU of the core over node blocks (bs_ok): the core is stored as Nc block ROWS, block row k =
+    // S rows of [ D_k | blocks (k, j) of the nodes eliminated after k | rhs_k | blocks of nodes eliminated before k ]
+    // (structurally nonzero blocks and fill only), and eliminated level by level of the elimination tree: the
+    // nodes of a level are independent and are factored concurrently, one warp each (bs_solve in yhb_kernels.cuh)
+    int bs_ok, bs_nlev, bs_total;
+    const int *bs_order;      // [Nc] elimination order (core positions)
+    const int *bs_pos;        // [Nc] position of a node in the order
+    const int *bs_level_ptr;  // [bs_nlev + 1] levels over bs_order
+    const int *bs_rowbase;    // [Nc] offset of block row k in the storage (doubles)
+    const int *bs_ld;         // [Nc] leading dimension of block row k (odd)
+    const int *bs_nlater;     // [Nc] blocks (k, j) with j eliminated after k
+    const int *bs_nblk;       // [Nc] blocks in block row k (diagonal included); rhs column = S * bs_nblk[k]... see bs_rhsoff
+    const int *bs_rhsoff;     // [Nc] column of rhs_k in block row k
+    const int *bs_coloff;     // [Nc][Nc] first column of block (k, j) in block row k, or -1
+    const int *bs_blkof;      // [Nc][Nc] node j of the slot-th block of block row k (slot 0 = k itself)
     // every table above points into one device blob; its first blob_hot_bytes hold what the Newton loop reads
     const char *blob;
     int blob_hot_bytes;
@@ -86,7 +101,8 @@ struct PlanDev {
     X(idft) X(dft) X(diode_nodes) X(bjt_nodes) X(cubic_nodes) X(dev_wave_base) X(pair_n) X(pair_m) X(pair_of) \
     X(row_ptr) X(row_pairs) X(pg_ptr) X(pg) X(pc_ptr) X(pc) X(ni_ptr) X(ni) X(nq_ptr) X(nq) X(core_rows)      \
     X(core_cols) X(core_col_of) X(a_row) X(a_col) X(a_sgn) X(a_ptr) X(a_pair) X(a_m) X(b_row) X(b_col)        \
-    X(b_sgn) X(b_ptr) X(b_pair) X(b_m) X(r_ptr) X(r_pair) X(r_m)
+    X(b_sgn) X(b_ptr) X(b_pair) X(b_m) X(r_ptr) X(r_pair) X(r_m) X(bs_order) X(bs_pos) X(bs_level_ptr) X(bs_rowbase)      \
+    X(bs_ld) X(bs_nlater) X(bs_nblk) X(bs_rhsoff) X(bs_coloff) X(bs_blkof)
 
 struct Plan {
     PlanDev d;                  // device view
