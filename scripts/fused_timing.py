@@ -38,8 +38,12 @@ tot = sum(t[k] for k in names)
 for k, nm in names.items():
     per = t[k] / (newton if k in (0, 5) else lus)
     print('%-14s %5.1f%% of CTA time, %8.0f cycles per %s' % (nm, 100 * t[k] / tot, per, 'iteration' if k in (0, 5) else 'solve'))
+if plan.block_sparse():
+    print('block-sparse core LU (%d levels), cycles per solve: factor %.0f, schur %.0f, back substitution %.0f'
+          % ((plan.block_sparse(),) + tuple(t[k] / lus for k in (8, 11, 12))))
 npanel = lus * 21
-print('per panel (Wc=84, 21 panels): factor %.0f cycles; barrier wait owner %.0f / next owner %.0f / others(sum over warps) %.0f; '
+if not plan.block_sparse():
+  print('per panel (Wc=84, 21 panels): factor %.0f cycles; barrier wait owner %.0f / next owner %.0f / others(sum over warps) %.0f; '
       'update next owner %.0f / others (sum over warps) %.0f' % tuple(t[k] / npanel for k in (8, 10, 11, 12, 13, 14)))
 print('evaluation sub-phases, cycles per iteration: idft %.0f, device sweep %.0f, current/waveform sums %.0f, dfts %.0f, residual+test %.0f'
       % tuple(t[k] / newton for k in (16, 17, 18, 19, 20)))

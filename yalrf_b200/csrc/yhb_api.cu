@@ -60,6 +60,15 @@ static FusedChoice fused_choice(const PlanDev &d) {
     FusedChoice f{false, 0, 0, 0};
     if (d.flags & YHB_FLAG_STAGED) return f;
     const int need = std::max(1, (d.Wc + 1 + 7) / 8);
+    if (d.bs_ok && !getenv("YHB_NO_BS_COMPACT")) {
+        // block-sparse plans: the compact variant (core in block-row storage, 256 threads) when three CTAs fit one SM
+        constexpr size_t lim3 = (228 * 1024) / 3 - 1024 - 1024;  // per-CTA reserve and the static __shared__
+        const size_t b = fused_smem_doubles<kFusedBsNT>(d, true) * sizeof(double);
+        if (b <= lim3) {
+            const size_t c = (fused_lin_cache_doubles(d) + 2) * sizeof(double);
+            return b + c <= lim3 ? FusedChoice{true, kFusedBsNT, b + c, 3} : FusedChoice{true, kFusedBsNT, b, 1};
+        }
+    }
     for (int hot = 1; hot >= 0; --hot) {
 #define YHB_CASE(t)                                                                 \
     if (need <= t) {                                                                \
@@ -535,6 +544,20 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
         const int Nc = d.Nc;
         bool same = Nc >= 2 && Nc <= 16 && S <= 32 && !(desc->flags & YHB_FLAG_NO_BLOCK_SPARSE);
         for (int r = 0; same && r < Nc; ++r) same = core_rows[r] == core_cols[r];
+        // pivoting stays inside the diagonal blocks, so every core node needs a conductance of its own on the
+        // diagonal: a nonlinear device or a resistor (a node held only by gyrators, capacitors or inductors has a
+        // zero or DC-singular diagonal block, e.g. the source rows of an unpeeled system: dense solve)
+        for (int r = 0; same && r < Nc; ++r) {
+            auto it = pair_id.find(std::make_pair(core_rows[r], core_rows[r]));
+            bool own = false;
+            if (it != pair_id.end()) {
+                const int p = it->second;
+                own = p < d.npair_nl;
+                if (p < (int)plin.rows.size())
+                    for (const Term &t : plin.rows[p]) own = own || pl->lin_kind[t.idx] == YHB_LIN_RESISTOR;
+            }
+            same = own;
+        }
         if (same) {
             std::vector<std::vector<char>> nz(Nc, std::vector<char>(Nc, 0));
             for (int r = 0; r < Nc; ++r) {
@@ -1041,11 +1064,14 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
         int per_sm = 0;                                                                                       \
         YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<t>, fused_threads(t), fsmem)); \
         const int grid = std::min(B, std::max(1, per_sm) * sms);                                              \
+        if (getenv("YHB_DEBUG"))                                                                              \
+            fprintf(stderr, "yhb: k_fused<%d> threads %d smem %d B, %d CTAs/SM, grid %d, block-sparse %d\n", t,   \
+                    fused_threads(t), fsmem, per_sm, grid, d.bs_ok);                                          \
         ProfScope ps(PK_FUSED, st);                                                                           \
         k_fused<t><<<grid, fused_threads(t), fsmem, st>>>(d, ws, ea, L.fc.hot);                                      \
     } break;
         switch (L.fc.NT) {
-            YHB_LAUNCH_FUSED(0) YHB_FOR_NT(YHB_LAUNCH_FUSED)
+            YHB_LAUNCH_FUSED(0) YHB_LAUNCH_FUSED(1) YHB_FOR_NT(YHB_LAUNCH_FUSED)
             default: set_error("no fused kernel for this core size"); return -4;
         }
 #undef YHB_LAUNCH_FUSED
