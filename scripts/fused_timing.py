@@ -39,8 +39,8 @@ for k, nm in names.items():
     per = t[k] / (newton if k in (0, 5) else lus)
     print('%-14s %5.1f%% of CTA time, %8.0f cycles per %s' % (nm, 100 * t[k] / tot, per, 'iteration' if k in (0, 5) else 'solve'))
 if plan.block_sparse():
-    print('block-sparse core LU (%d levels), cycles per solve: factor %.0f, schur %.0f, back substitution %.0f'
-          % ((plan.block_sparse(),) + tuple(t[k] / lus for k in (8, 11, 12))))
+    print('block-sparse core LU (%d levels), cycles per solve: factor level 0 %.0f, deeper levels %.0f, schur %.0f, back substitution %.0f'
+          % ((plan.block_sparse(),) + tuple(t[k] / lus for k in (8, 9, 11, 12))))
 npanel = lus * 21
 if not plan.block_sparse():
   print('per panel (Wc=84, 21 panels): factor %.0f cycles; barrier wait owner %.0f / next owner %.0f / others(sum over warps) %.0f; '

@@ -536,7 +536,7 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     // ---- block-sparse LU structure of the core (PlanDev::bs_*): ordering by levels of independent minimum-degree
     // nodes, fill, block-row storage map
     std::vector<int> bs_order, bs_pos, bs_level_ptr(1, 0), bs_rowbase, bs_ld, bs_nlater, bs_nblk, bs_rhsoff, bs_coloff,
-        bs_blkof;
+        bs_blkof, bs_below_ptr(1, 0), bs_below;
     d.bs_ok = 0;
     d.bs_nlev = 0;
     d.bs_total = 0;
@@ -634,9 +634,14 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
                 for (int j : earlier) put(j);
                 bs_nlater[k] = (int)later.size();
                 bs_nblk[k] = slot;
-                bs_ld[k] = col | 1;
+                bs_ld[k] = col | 1;  // odd: conflict-free column walks
                 bs_rowbase[k] = (int)total;
                 total += (size_t)S * bs_ld[k];
+            }
+            for (int k = 0; k < Nc; ++k) {  // block rows that still hold a block (i, k) when k is eliminated
+                for (int i = 0; i < Nc; ++i)
+                    if (bs_pos[i] > bs_pos[k] && nz[i][k]) bs_below.push_back(i);
+                bs_below_ptr.push_back((int)bs_below.size());
             }
             const bool sparse = nnz1 < Nc * Nc;
             // never more than the dense matrix of the fused engine; the pivot permutations ([Nc][32] ints) take the
@@ -730,13 +735,22 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     pc.flatten(d.npair_nl, ptr_pc, t_pc); UP(pc_ptr, ptr_pc); UP(pc, t_pc);
     ni.flatten(N, ptr_ni, t_ni); UP(ni_ptr, ptr_ni); UP(ni, t_ni);
     nq.flatten(N, ptr_nq, t_nq); UP(nq_ptr, ptr_nq); UP(nq, t_nq);
+    // core node blocks that hold a pair: (row node, column node, pair), the work list of the core assembly
+    std::vector<int> cblk;
+    for (int r = 0; r < d.Nc; ++r)
+        for (int c = 0; c < d.Nc; ++c) {
+            auto it = pair_id.find(std::make_pair(core_rows[r], core_cols[c]));
+            if (it != pair_id.end()) { cblk.push_back(r); cblk.push_back(c); cblk.push_back(it->second); }
+        }
+    d.ncblk = (int)cblk.size() / 3;
+    UP(cblk, cblk);
     UP(core_rows, core_rows); UP(core_cols, core_cols); UP(core_col_of, core_col_of);
     UP(a_row, a_row); UP(a_col, a_col); UP(a_sgn, a_sgn); UP(a_ptr, a_ptr); UP(a_pair, a_pair); UP(a_m, a_m);
     UP(b_row, b_row); UP(b_col, b_col); UP(b_sgn, b_sgn); UP(b_ptr, b_ptr); UP(b_pair, b_pair); UP(b_m, b_m);
     UP(r_ptr, r_ptr); UP(r_pair, r_pair); UP(r_m, r_m);
     UP(bs_order, bs_order); UP(bs_pos, bs_pos); UP(bs_level_ptr, bs_level_ptr); UP(bs_rowbase, bs_rowbase);
     UP(bs_ld, bs_ld); UP(bs_nlater, bs_nlater); UP(bs_nblk, bs_nblk); UP(bs_rhsoff, bs_rhsoff);
-    UP(bs_coloff, bs_coloff); UP(bs_blkof, bs_blkof);
+    UP(bs_coloff, bs_coloff); UP(bs_blkof, bs_blkof); UP(bs_below_ptr, bs_below_ptr); UP(bs_below, bs_below);
     d.blob_hot_bytes = (int)align_up(blob.size(), 16);
     // k_prepare / k_dc only
     UP(bin_k1, pl->bin_k1);

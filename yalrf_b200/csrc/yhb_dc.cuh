@@ -730,7 +730,10 @@ struct DcWarp {
 };
 
 template <int MMAX>
-__global__ void __launch_bounds__(32) k_dc_warp(PlanDev P, DcArgs a, int batch) {
+#ifndef YHB_DC_WARP_MINBLOCKS
+#define YHB_DC_WARP_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P, DcArgs a, int batch) {
     extern __shared__ double smw[];
     const int b = blockIdx.x;
     if (b >= batch) return;

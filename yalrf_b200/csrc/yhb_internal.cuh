@@ -80,12 +80,16 @@ struct PlanDev {
     // S rows of [ D_k | blocks (k, j) of the nodes eliminated after k | rhs_k | blocks of nodes eliminated before k ]
     // (structurally nonzero blocks and fill only), and eliminated level by level of the elimination tree: the
     // nodes of a level are independent and are factored concurrently, one warp each (bs_solve in yhb_kernels.cuh)
+    int ncblk;                // core node blocks that hold a pair
+    const int *cblk;          // [ncblk][3] row node, column node (core positions), pair
     int bs_ok, bs_nlev, bs_total;
     const int *bs_order;      // [Nc] elimination order (core positions)
     const int *bs_pos;        // [Nc] position of a node in the order
     const int *bs_level_ptr;  // [bs_nlev + 1] levels over bs_order
     const int *bs_rowbase;    // [Nc] offset of block row k in the storage (doubles)
     const int *bs_ld;         // [Nc] leading dimension of block row k (odd)
+    const int *bs_below_ptr;  // [Nc + 1] CSR over bs_below
+    const int *bs_below;      // block rows i (eliminated after k) that hold a block (i, k)
     const int *bs_nlater;     // [Nc] blocks (k, j) with j eliminated after k
     const int *bs_nblk;       // [Nc] blocks in block row k (diagonal included); rhs column = S * bs_nblk[k]... see bs_rhsoff
     const int *bs_rhsoff;     // [Nc] column of rhs_k in block row k
@@ -102,7 +106,7 @@ struct PlanDev {
     X(row_ptr) X(row_pairs) X(pg_ptr) X(pg) X(pc_ptr) X(pc) X(ni_ptr) X(ni) X(nq_ptr) X(nq) X(core_rows)      \
     X(core_cols) X(core_col_of) X(a_row) X(a_col) X(a_sgn) X(a_ptr) X(a_pair) X(a_m) X(b_row) X(b_col)        \
     X(b_sgn) X(b_ptr) X(b_pair) X(b_m) X(r_ptr) X(r_pair) X(r_m) X(bs_order) X(bs_pos) X(bs_level_ptr) X(bs_rowbase)      \
-    X(bs_ld) X(bs_nlater) X(bs_nblk) X(bs_rhsoff) X(bs_coloff) X(bs_blkof)
+    X(bs_ld) X(bs_nlater) X(bs_nblk) X(bs_rhsoff) X(bs_coloff) X(bs_blkof) X(bs_below_ptr) X(bs_below) X(cblk)
 
 struct Plan {
     PlanDev d;                  // device view
