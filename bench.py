@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 
 GRID = 64
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused launch over the 4096-point grid (ncu --set full, profiles/)
-FUSED_TRAFFIC_BYTES = {'diffamp': 48572160, 'activeload': None}
+FUSED_TRAFFIC_BYTES = {'diffamp': 49319936, 'activeload': None}
 
 
 def grid_points(rank, world, workload):
@@ -282,14 +282,17 @@ def run_gpu(args):
                          'note': 'FP64 pipes (DFMA + DMMA).  achieved = SURVEY 8d algorithmic LU flops (2/3 W^3 + 2 W^2, '
                                  'W=%d, the system the reference hands to LAPACK) x factorisations / CUDA-event time of '
                                  'the whole fused kernel (which also does device evaluation, the DFTs, assembly and the '
-                                 'peeled rows); achieved_executed counts the Wc=%d core that structural peeling leaves '
-                                 '(the kernel executes Wc^3 multiply-adds per solve as a Gauss-Jordan elimination, its '
-                                 'trailing updates on the FP64 tensor pipe).  peak = DFMA microbenchmark run live '
+                                 'peeled rows): the fraction says how much of the reference\'s arithmetic the structure '
+                                 'removes, not how busy the pipe is.  achieved_executed counts a dense factorisation of '
+                                 'the Wc=%d core that structural peeling leaves; the block-sparse LU over node blocks '
+                                 'that k_fused<1> runs on it executes about 1/8 of that again (DiffAmp: 3 + 1 node blocks '
+                                 'of 21 pivots on 10 of 16 blocks).  peak = DFMA microbenchmark run live '
                                  '(MEASURED_PEAKS.json has no fp64 figure; DMMA m8n8k4 measured at 36.8 TFLOP/s, '
-                                 'profiles/r01_microbench.txt).  ncu (profiles/r01_bench_fused_full.txt): DMMA pipe '
-                                 'active 9.1 %%, FP64 pipe 5.3 %%, issue slots 29 %%: the kernel is bound by the serial '
-                                 'pivot chain at 2 resident circuits per SM.  traffic = dram bytes of one launch from '
-                                 'ncu --set full.' % (W, wc)})
+                                 'profiles/r01_microbench.txt).  ncu (profiles/r01_bench_fused_full.txt): issue slots '
+                                 '42.6 %% busy, FP64 pipe 8.9 %%, DMMA pipe 2.6 %% (transforms), 3 CTAs/SM by shared '
+                                 'memory and registers: the kernel is bound by the dependent-issue latency of the '
+                                 'factorisation warps.  traffic = dram bytes of one launch from ncu --set full.'
+                                 % (W, wc)})
         else:
             hbm = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(
                 os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0

@@ -8,7 +8,7 @@ names_file = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, 'profiles'
 names = []
 for line in open(names_file):
     t = line.split()
-    if t and not line.startswith('#') and ('__' in t[0] or t[0].startswith('launch')):
+    if t and not line.startswith('#') and ('__' in t[0] or t[0].startswith('launch')) and t[0] not in names:
         names.append(t[0])
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))

@@ -634,7 +634,11 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
                 for (int j : earlier) put(j);
                 bs_nlater[k] = (int)later.size();
                 bs_nblk[k] = slot;
+#ifdef YHB_BS_VEC
+                bs_ld[k] = (col + 1) & ~1;
+#else
                 bs_ld[k] = col | 1;  // odd: conflict-free column walks
+#endif
                 bs_rowbase[k] = (int)total;
                 total += (size_t)S * bs_ld[k];
             }
@@ -644,9 +648,8 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
                 bs_below_ptr.push_back((int)bs_below.size());
             }
             const bool sparse = nnz1 < Nc * Nc;
-            // never more than the dense matrix of the fused engine; the pivot permutations ([Nc][32] ints) take the
-            // place of the pair spectra during the solve
-            const bool fits = total <= (size_t)(d.Wc + 1) * (d.Wc + 1) && (size_t)Nc * 16 <= (size_t)d.npair_nl * 2 * S;
+            // never more than the dense matrix of the fused engine
+            const bool fits = total <= (size_t)(d.Wc + 1) * (d.Wc + 1);
             if (fits && (sparse || (desc->flags & YHB_FLAG_BLOCK_SPARSE))) {
                 d.bs_ok = 1;
                 d.bs_nlev = (int)bs_level_ptr.size() - 1;
