@@ -634,11 +634,7 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
                 for (int j : earlier) put(j);
                 bs_nlater[k] = (int)later.size();
                 bs_nblk[k] = slot;
-#ifdef YHB_BS_VEC
-                bs_ld[k] = (col + 1) & ~1;
-#else
                 bs_ld[k] = col | 1;  // odd: conflict-free column walks
-#endif
                 bs_rowbase[k] = (int)total;
                 total += (size_t)S * bs_ld[k];
             }
