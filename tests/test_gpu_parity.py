@@ -443,6 +443,29 @@ def test_block_sparse_core_lu(yb, golden, mode):
         assert relmax(hb.V, g['V']) < 1e-9, (tag, mode)
 
 
+@pytest.mark.parametrize('stages,nh,ac', [(4, [1, 1], 1.0), (6, [1, 1], 1.0), (5, [2, 1], 0.5)])
+def test_block_sparse_chain_vs_oracle(yb, stages, nh, ac):
+    """Short diode / BJT ladders on the fused engine: the core is a chain of node blocks, eliminated from both ends
+    towards the middle (three and more levels, blocks of earlier AND later nodes in one block row).  Block-sparse
+    and dense core solves against the oracle on the same inputs."""
+    from oracle import hb_oracle as ho
+    yo = ho.FlatNetlist()
+    circuits.ladder(yo, stages=stages, cje=0.0, ac=ac)
+    o = ho.HBOracle('HB1', [1.1e6, 0.9e6], nh)
+    conv_o = o.run(yo)[0]
+    for mode in (None, False):
+        y = yb.Netlist('ladder')
+        h = circuits.ladder(y, stages=stages, cje=0.0, ac=ac)
+        hb = mthb('HB1', h['freq'], nh)
+        hb.block_sparse = mode
+        conv, freqs, Vf, _, _ = hb.run(y)
+        assert hb._plan.engine() == 'fused'
+        assert hb._plan.block_sparse() >= 3 if mode is None else hb._plan.block_sparse() == 0
+        assert conv == conv_o
+        assert hb.last.levels() == [l[1] for l in o.level_log], mode
+        assert relmax(hb.V, o.V) < 1e-9, mode
+
+
 # ----------------------------------------------------------------------------- more reference scripts
 @pytest.mark.parametrize('tag,builder,nh', [('current_mirror', 'current_mirror', None),
                                             ('fullwave_rectifier', 'fullwave_rectifier', None),
