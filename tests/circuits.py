@@ -251,3 +251,17 @@ def add_probe(y, name, node, f, amp):
     y.add_iac(name + '.I.Oscprobe', name + '.nosc1', 'gnd', ac=amp, freq=f)
     y.add_gyrator(name + '.G.Oscprobe', name + '.nosc1', name + '.nosc2', 'gnd', 'gnd', 1)
     return y.add_idealharmonicfilter(name + 'IHF.Oscprobe', name + '.nosc2', node, f)
+
+
+def ring(y, n=4, ac=0.5, seed=1):
+    """Not a reference script: a ring of n nodes (resistors around, a diode to ground at every node) behind a source
+    resistor.  Eliminating a ring node couples its two neighbours: the smallest core whose block-sparse LU has FILL."""
+    rng = np.random.default_rng(seed)
+    y.add_iac('I1', 'nx', 'gnd', ac=ac, freq=1e6)
+    y.add_gyrator('G1', 'nx', 'ns', 'gnd', 'gnd', 1)
+    y.add_resistor('Rs', 'ns', 'n1', 50)
+    for i in range(1, n + 1):
+        y.add_resistor('R%d' % i, 'n%d' % i, 'n%d' % (i % n + 1), 100 + 10 * i)
+        d = y.add_diode('D%d' % i, 'n%d' % i, 'gnd')
+        d.options['Is'] = 1e-15 * float(10.0 ** rng.uniform(-0.05, 0.05))
+    return dict(freq=1e6, K=4)

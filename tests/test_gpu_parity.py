@@ -466,6 +466,29 @@ def test_block_sparse_chain_vs_oracle(yb, stages, nh, ac):
         assert relmax(hb.V, o.V) < 1e-9, mode
 
 
+@pytest.mark.parametrize('n,ac', [(4, 0.5), (6, 1.0)])
+def test_block_sparse_fill_vs_oracle(yb, n, ac):
+    """A ring of diode nodes: eliminating a ring node couples its two neighbours, so the block-row storage holds FILL
+    blocks (zeroed before the assembly, created by the Schur updates).  Block-sparse and dense core solves against
+    the oracle on the same inputs."""
+    from oracle import hb_oracle as ho
+    yo = ho.FlatNetlist()
+    h = circuits.ring(yo, n=n, ac=ac)
+    o = ho.HBOracle('HB1', h['freq'], h['K'])
+    conv_o = o.run(yo)[0]
+    for mode in (None, False):
+        y = yb.Netlist('ring')
+        circuits.ring(y, n=n, ac=ac)
+        hb = mthb('HB1', h['freq'], h['K'])
+        hb.block_sparse = mode
+        conv, freqs, Vf, _, _ = hb.run(y)
+        assert hb._plan.engine() == 'fused' and hb._plan.core()[0] == n
+        assert (hb._plan.block_sparse() >= 2) if mode is None else hb._plan.block_sparse() == 0
+        assert conv == conv_o
+        assert hb.last.levels() == [l[1] for l in o.level_log], mode
+        assert relmax(hb.V, o.V) < 1e-9, mode
+
+
 # ----------------------------------------------------------------------------- more reference scripts
 @pytest.mark.parametrize('tag,builder,nh', [('current_mirror', 'current_mirror', None),
                                             ('fullwave_rectifier', 'fullwave_rectifier', None),

@@ -540,6 +540,7 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     d.bs_ok = 0;
     d.bs_nlev = 0;
     d.bs_total = 0;
+    d.bs_zero = 1;
     {
         const int Nc = d.Nc;
         bool same = Nc >= 2 && Nc <= 16 && S <= 32 && !(desc->flags & YHB_FLAG_NO_BLOCK_SPARSE);
@@ -651,7 +652,7 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
                 d.bs_nlev = (int)bs_level_ptr.size() - 1;
                 d.bs_total = (int)total;
             }
-            (void)nnz0;
+            d.bs_zero = nnz1 != nnz0;  // fill blocks hold no pair: only then the storage needs zeroing before assembly
         }
     }
     d.nA = (int)a_row.size();

@@ -82,7 +82,7 @@ struct PlanDev {
     // nodes of a level are independent and are factored concurrently, one warp each (bs_solve in yhb_kernels.cuh)
     int ncblk;                // core node blocks that hold a pair
     const int *cblk;          // [ncblk][3] row node, column node (core positions), pair
-    int bs_ok, bs_nlev, bs_total;
+    int bs_ok, bs_nlev, bs_total, bs_zero;
     const int *bs_order;      // [Nc] elimination order (core positions)
     const int *bs_pos;        // [Nc] position of a node in the order
     const int *bs_level_ptr;  // [bs_nlev + 1] levels over bs_order
