@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 
 GRID = 64
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused launch over the 4096-point grid (ncu --set full, profiles/)
-FUSED_TRAFFIC_BYTES = {'diffamp': 48629760, 'activeload': None}
+FUSED_TRAFFIC_BYTES = {'diffamp': 49096192, 'activeload': None}
 
 
 def grid_points(rank, world, workload):
@@ -289,7 +289,7 @@ def run_gpu(args):
                                  'of 21 pivots on 10 of 16 blocks).  peak = DFMA microbenchmark run live '
                                  '(MEASURED_PEAKS.json has no fp64 figure; DMMA m8n8k4 measured at 36.8 TFLOP/s, '
                                  'profiles/r01_microbench.txt).  ncu (profiles/r01_bench_fused_full.txt): issue slots '
-                                 '42.6 %% busy, FP64 pipe 8.9 %%, DMMA pipe 2.6 %% (transforms), 3 CTAs/SM by shared '
+                                 '39 %% busy, FP64 pipe 9.2 %%, DMMA pipe 2.7 %% (transforms), 3 CTAs/SM by shared '
                                  'memory and registers: the kernel is bound by the dependent-issue latency of the '
                                  'factorisation warps.  traffic = dram bytes of one launch from ncu --set full.'
                                  % (W, wc)})
