@@ -64,6 +64,9 @@ static FusedChoice fused_choice(const PlanDev &d) {
         // block-sparse plans: the compact variant (core in block-row storage, 256 threads) when three CTAs fit one SM
         constexpr size_t lim3 = (228 * 1024) / 3 - 1024 - 1024;  // per-CTA reserve and the static __shared__
         const size_t b = fused_smem_doubles<kFusedBsNT>(d, true) * sizeof(double);
+        if (getenv("YHB_DEBUG"))
+            fprintf(stderr, "yhb: compact block-sparse variant needs %zu B of %zu (block rows %d doubles, %d levels, hot tables %d B, "
+                    "%d nonlinear pairs)\n", b, lim3, d.bs_total, d.bs_nlev, d.blob_hot_bytes, d.npair_nl);
         if (b <= lim3) {
             const size_t c = (fused_lin_cache_doubles(d) + 2) * sizeof(double);
             return b + c <= lim3 ? FusedChoice{true, kFusedBsNT, b + c, 3} : FusedChoice{true, kFusedBsNT, b, 1};
