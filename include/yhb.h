@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YHB_VERSION 100
+#define YHB_VERSION 200
 
 /* linear element kinds: the classes that implement add_mthb_stamps (MultiToneHarmonicBalance.py:686-695) */
 enum {
@@ -79,7 +79,11 @@ enum {
 
 #define YHB_MAX_LEVELS 64 /* hb_loop calls recorded per solve: 1 direct attempt + <=50 continuation levels */
 
-typedef struct yhb_plan yhb_plan; /* opaque: topology + tables, immutable, shareable across streams */
+typedef struct yhb_plan yhb_plan; /* opaque: topology + device tables of one netlist shape.  The tables are immutable, but a
+                                     plan also owns mutable scratch (the pinned counters of the launch loop, the staging
+                                     buffer and stream of the *_host entry points): calls on ONE plan serialise on an
+                                     internal mutex.  Use one plan per host thread / stream for concurrency.  A plan
+                                     belongs to the CUDA device that was current when it was created. */
 
 /* Topology of one netlist shape (what Netlist + run()'s setup :234-302 determine).  Host pointers. */
 typedef struct {
@@ -127,8 +131,12 @@ typedef struct {
     int32_t reserved;
 } yhb_options;
 
-/* Results of a solve.  Any pointer may be NULL to skip that output. */
+/* Results of a solve.  Any pointer may be NULL to skip that output.
+ * struct_size MUST be set to sizeof(yhb_result) by the caller: the library reads only that many bytes and treats
+ * the fields beyond them as NULL, so a binding written against an older header keeps working (and a binding that
+ * forgets the field fails loudly with "yhb_result.struct_size not set" instead of reading past the struct). */
 typedef struct {
+    size_t struct_size;
     double *V;             /* [B][W]  in: start vector when have_v0, out: hb.V (:393)                  */
     double *Vf;            /* [B][N][K+1][2]  complex phasors hb.Vf (:396-403)                         */
     int32_t *converged;    /* [B]                                                                     */
@@ -138,6 +146,8 @@ typedef struct {
     double *level_alpha;   /* [B][YHB_MAX_LEVELS]  'Alpha level' of each call (1.0 for the direct attempt) */
     double *err;           /* [B]  'HB total error' sum|F| of the last hb_loop call (:597)             */
     double *Inl;           /* [B][W]  nonlinear current spectrum fft(it) + Omega fft(qt) (:584) at the returned V   */
+    double *Ic;            /* [B][num_bjt][S]  collector-current samples of the last evaluation: the reference's
+                              dev.Ic side channel (:512), read by tests/ColpittsCB_Analysis.py:96-101               */
 } yhb_result;
 
 const char *yhb_last_error(void);

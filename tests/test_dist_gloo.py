@@ -1,5 +1,5 @@
-"""World-size-2 (and 3) gloo tests of the multi-GPU path on CPU: contiguous sharding of a batch over ranks and the
-single end-of-solve gather.  The GPU solve itself is replaced by a deterministic stand-in (there is no CPU
+"""World-size-2 (and 3) gloo tests of the multi-GPU path on CPU: round-robin sharding of a batch over ranks
+(circuit b -> rank b % world) and the single packed end-of-solve gather.  The GPU solve itself is replaced by a deterministic stand-in (there is no CPU
 fallback); what is tested is the host logic every rank runs around it."""
 import os
 import socket
@@ -29,7 +29,10 @@ def _fake_run(plan, pb, options, V0):
     res.Vf[:] = (key[:, None, None] * (1 + 2j))
     res.converged[:] = 1
     res.newton_iters[:] = np.round(key * 1e4).astype(np.int32)
+    res.level_iters[:] = 0
     res.level_iters[:, 0] = 3
+    res.level_alpha[:] = 0.25
+    res.lu_count[:] = 7
     res.err[:] = key
     return res
 
@@ -51,10 +54,12 @@ def _worker(rank, world, port, B, out):
     pb = ParamBlock(topo, 10e6, B)
     pb.set(h['i2'], 'ac', np.linspace(1e-3, 2e-3, B))
     res = _dist.run_block_distributed(FakePlan, pb, {}, None, run_fn=_fake_run)
-    lo, hi = _dist.shard_bounds(B, rank, world)
+    idx = _dist.shard_indices(B, rank, world)
     if rank == 0:
-        np.savez(out, V=res.V, Vf=res.Vf, it=res.newton_iters, conv=res.converged, err=res.err)
-    assert hi - lo in (B // world, B // world + 1)
+        np.savez(out, V=res.V, Vf=res.Vf, it=res.newton_iters, conv=res.converged, err=res.err, lev=res.level_iters,
+                 alpha=res.level_alpha, lu=res.lu_count)
+    assert len(idx) == _dist.shard_count(B, rank, world) and len(idx) in (B // world, B // world + 1)
+    assert res.converged.dtype == np.int32 and res.level_iters.dtype == np.int32
     dist.barrier()
     dist.destroy_process_group()
 
@@ -69,13 +74,18 @@ def test_shard_and_gather(tmp_path, world, B):
     np.testing.assert_allclose(g['Vf'], np.broadcast_to(key[:, None, None] * (1 + 2j), (B, 10, 11)), rtol=1e-15)
     assert g['conv'].tolist() == [1] * B
     np.testing.assert_array_equal(g['it'], np.round(key * 1e4).astype(np.int32))
+    np.testing.assert_array_equal(g['lev'][:, :2], np.tile([3, 0], (B, 1)))
+    np.testing.assert_array_equal(g['alpha'], np.full((B, 64), 0.25))
+    np.testing.assert_array_equal(g['lu'], np.full(B, 7))
+    np.testing.assert_array_equal(g['err'], key)
 
 
-def test_shard_bounds_cover_everything():
-    from yalrf_b200._dist import shard_bounds
+def test_shards_cover_everything():
+    from yalrf_b200._dist import shard_count, shard_indices
     for B in (0, 1, 5, 64, 4096, 4097):
         for world in (1, 2, 3, 8):
-            spans = [shard_bounds(B, r, world) for r in range(world)]
-            assert spans[0][0] == 0 and spans[-1][1] == B
-            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
-            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+            parts = [shard_indices(B, r, world) for r in range(world)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(B))
+            assert [len(p) for p in parts] == [shard_count(B, r, world) for r in range(world)]
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            assert shard_count(B, 0, world) == max(len(p) for p in parts)

@@ -597,3 +597,130 @@ def test_ladder_golden(yb, golden, tag, stages, nh, bt):
     assert hb.last.levels() == g['iters'].tolist()
     if conv:
         assert relmax(hb.V, g['V']) < 1e-9
+
+
+# ----------------------------------------------------------------------------- boundary
+def _integration_stub():
+    """the python code block of INTEGRATION.md section 2, verbatim, bound to this repo's device classes and library"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, 'INTEGRATION.md')).read()
+    sec = md[md.index('## 2. Bind the C ABI'):]
+    code = re.search(r'```python\n(.*?)```', sec, re.S).group(1)
+    assert 'def run(self, netlist, V0=None):' in code
+    # the stub targets the reference package; the host mirror has the same class names
+    code = code.replace('from yalrf.Devices import *', 'from yalrf_b200.Devices import *')
+    from yalrf_b200 import _lib
+    os.environ['YHB_LIB'] = _lib.LIB_PATH
+    ns = {}
+    exec(compile(code, 'INTEGRATION.md', 'exec'), ns)
+    return ns
+
+
+def test_integration_stub_verbatim(yb, golden):
+    """A maintainer's binding written from include/yhb.h + INTEGRATION.md alone: HB_Diode through it reproduces the
+    unmodified reference (iteration path included: the phasors agree to 1e-9)."""
+    ns = _integration_stub()
+
+    class RefLikeHB:                       # the attributes the reference class has before run() (:25-30)
+        def __init__(self, name, freq, numharmonics):
+            self.name, self.freq, self.numharmonics = name, freq, numharmonics
+            self.options = {'reltol': 1e-3, 'abstol': 1e-6, 'maxiter': 100}
+    RefLikeHB.run = ns['run']
+    g = golden('hb_diode')
+    y = yb.YalRF('Diode Testbench')
+    h = circuits.hb_diode(y)
+    hb = RefLikeHB('HB1', h['freq'], h['K'])
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv
+    assert relmax(hb.V, g['V']) < 1e-9 and relmax(Vf, g['Vf']) < 1e-9
+    np.testing.assert_array_equal(freqs, g['freqs'])
+    assert np.array_equal(hb.IDFT, g['IDFT']) and np.array_equal(hb.DFT, g['DFT'])
+    # warm restart through the stub (:330-335): one hb_loop from the converged point
+    conv2, _, Vf2, _, _ = hb.run(y, hb.V)
+    assert conv2 and relmax(Vf2, g['Vf']) < 1e-6
+    # two tones and a BJT circuit through the same stub
+    g2 = golden('two_tones_3x3')
+    y2 = yb.YalRF('Diode Testbench')
+    h2 = circuits.hb_diode_two_tones(y2)
+    hb2 = RefLikeHB('HB1', h2['freq'], [3, 3])
+    conv, freqs, Vf, _, _ = hb2.run(y2)
+    assert conv and relmax(hb2.V, g2['V']) < 1e-9
+    np.testing.assert_allclose(freqs, g2['freqs'], rtol=1e-15)
+
+
+def test_result_struct_size_is_checked(yb):
+    """yhb_result without struct_size is refused (no read past the caller's struct); a SHORTER struct from an older
+    header works, its missing fields are treated as NULL."""
+    from yalrf_b200 import _engine as E, _lib as L
+    from yalrf_b200._flatten import ParamBlock
+    y = yb.YalRF('Diode Testbench')
+    h = circuits.hb_diode(y)
+    plan, topo = E.get_plan(y, h['freq'], h['K'])
+    pb = ParamBlock(topo, h['freq'], 1).finalize()
+    p, o = E.make_params(pb), E.make_options({'reltol': 1e-3, 'abstol': 1e-6, 'maxiter': 100})
+    V = np.zeros(plan.W)
+    conv = np.zeros(1, dtype=np.int32)
+    lib = L.lib()
+    r = L.Result()
+    r.struct_size = 0
+    r.V, r.converged = V.ctypes.data, conv.ctypes.data
+    assert lib.yhb_run_host(plan.handle, C.byref(p), C.byref(o), None, C.byref(r)) == -1
+    assert b'struct_size' in lib.yhb_last_error()
+
+    class OldResult(C.Structure):          # round-1 layout + struct_size: no Inl, no Ic
+        _fields_ = [('struct_size', C.c_size_t)] + [(n, C.c_void_p) for n in
+                    ('V', 'Vf', 'converged', 'newton_iters', 'lu_count', 'level_iters', 'level_alpha', 'err')]
+    ro = OldResult()
+    ro.struct_size = C.sizeof(OldResult)
+    ro.V, ro.converged = V.ctypes.data, conv.ctypes.data
+    rc = lib.yhb_run_host(plan.handle, C.byref(p), C.byref(o), None, C.cast(C.byref(ro), C.POINTER(L.Result)))
+    assert rc == 0, lib.yhb_last_error()
+    assert conv[0] == 1 and abs(V[plan.S * 1]) > 0.1
+
+
+def test_bjt_ic_side_channel(yb):
+    """dev.Ic after run() (:512): the collector-current samples of the last evaluation, against the oracle's."""
+    from oracle import hb_oracle as ho
+    y = yb.YalRF('x')
+    h = circuits.diffamp(y, vin=5e-3)
+    hb = mthb('HB1', h['freq'], h['K'])
+    assert hb.run(y)[0]
+    yo = ho.FlatNetlist()
+    ho_h = circuits.diffamp(yo, vin=5e-3)
+    o = ho.HBOracle('HB1', h['freq'], h['K'])
+    assert o.run(yo)[0]
+    assert relmax(hb.V, o.V) < 1e-9
+    for q, qo in zip(h['q'], ho_h['q']):
+        assert q.Ic.shape == (hb.S,)
+        assert relmax(q.Ic, np.asarray(qo.Ic).ravel()) < 1e-8
+
+
+def test_swept_tone_moves_harmonic_filters(yb):
+    """run_sweep(freq=...): an IdealHarmonicFilter at the nominal tone follows the swept tone (its exact-equality test,
+    IdealHarmonicFilter.py:34, would otherwise miss at every swept point and the filter would be 1e-12 S everywhere)."""
+    fs = np.array([0.9e6, 1.0e6, 1.1e6])
+    y = yb.YalRF('x')
+    i1 = y.add_iac('I1', 'nx', 'gnd', ac=1.0, freq=1e6)
+    y.add_gyrator('G1', 'nx', 'n1', 'gnd', 'gnd', 1)
+    y.add_idealharmonicfilter('F1', 'n1', 'n2', 1e6)
+    y.add_resistor('R1', 'n2', 'gnd', 50.0)
+    d1 = y.add_diode('D1', 'n2', 'gnd')
+    hb = mthb('HB1', 1e6, 5)
+    res = hb.run_sweep(y, [(i1, 'ac', np.ones(3))], freq=fs)
+    assert res.converged.all()
+    ref = []
+    for f in fs:                            # the same points one by one, every frequency-bearing attribute set by hand
+        y2 = yb.YalRF('x')
+        y2.add_iac('I1', 'nx', 'gnd', ac=1.0, freq=float(f))
+        y2.add_gyrator('G1', 'nx', 'n1', 'gnd', 'gnd', 1)
+        y2.add_idealharmonicfilter('F1', 'n1', 'n2', float(f))
+        y2.add_resistor('R1', 'n2', 'gnd', 50.0)
+        y2.add_diode('D1', 'n2', 'gnd')
+        hb2 = mthb('HB1', float(f), 5)
+        assert hb2.run(y2)[0]
+        ref.append(hb2.V[:, 0])
+    assert relmax(res.V, np.array(ref)) < 1e-12
+    n2 = y.get_node_idx('n2') - 1
+    assert np.all(np.abs(res.Vf[:, n2, 1]) > 0.3)      # the fundamental passes the filter at every swept point

@@ -20,7 +20,7 @@ def test_library_exports_header_symbols():
     assert names >= set(_lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.yhb_version() == 100
+    assert lib.yhb_version() == 200
     assert _lib.DIODE_NPAR == 10 and _lib.BJT_NPAR == 32
 
 
@@ -109,3 +109,37 @@ def test_dft_tables_match_reference_fixture(golden):
     IDFT, DFT = dft_tables(10)
     assert np.array_equal(IDFT, g['IDFT'])
     assert np.array_equal(DFT, g['DFT'])
+
+
+def _struct_fields(hdr, name):
+    end = hdr.index('} ' + name + ';')
+    body = hdr[hdr.rindex('typedef struct {', 0, end) + len('typedef struct {'):end]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    out = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if decl:
+            for nm in decl.split(','):
+                out.append(re.sub(r'[^A-Za-z0-9_]', ' ', nm).split()[-1])
+    return out
+
+
+def test_binding_and_integration_stub_match_header_structs():
+    """ctypes structs of the host mirror AND of the maintainer stub in INTEGRATION.md have the header's fields, in the
+    header's order (a struct with a missing tail field is exactly the undefined behaviour round 1 shipped)."""
+    import ctypes
+    from yalrf_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'yhb.h')).read()
+    md = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    code = re.search(r'```python\n(.*?)```', md[md.index('## 2. Bind the C ABI'):], re.S).group(1)
+    code = code.replace('from yalrf.Devices import *', 'from yalrf_b200.Devices import *')
+    os.environ['YHB_LIB'] = _lib.LIB_PATH
+    ns = {}
+    exec(compile(code, 'INTEGRATION.md', 'exec'), ns)
+    for cname, pyname in [('yhb_result', 'Result'), ('yhb_params', 'Params'), ('yhb_options', 'Options'),
+                          ('yhb_plan_desc', 'PlanDesc')]:
+        want = _struct_fields(hdr, cname)
+        for cls in (getattr(_lib, pyname), ns[pyname]):
+            assert [f[0] for f in cls._fields_] == want, (cname, cls)
+        assert ctypes.sizeof(getattr(_lib, pyname)) == ctypes.sizeof(ns[pyname])
+    assert _lib.Result().struct_size == ctypes.sizeof(_lib.Result) == 8 * 11

@@ -37,6 +37,7 @@ class MultiToneHarmonicBalance:
         self.block_sparse = None      # fused engine: None = block-sparse LU over node blocks when the core's block
                                       # structure is sparse, True / False = whenever it applies / never (dense solve)
         self.distributed = False      # run_batch / run_sweep: shard the circuits over torch.distributed ranks, gather
+        self.report_levels = True     # run_batch / run_sweep: copy the per-level reports back (768 B per circuit)
         self.last = None              # BatchResult of the last call
 
     # ------------------------------------------------------------------ helpers
@@ -96,9 +97,13 @@ class MultiToneHarmonicBalance:
         plan, topo = self._setup(netlist)
         pb = ParamBlock(topo, self.freq, 1)
         self._had_v0 = V0 is not None
-        res = E.run_host(plan, pb, self.options, None if V0 is None else np.asarray(V0, dtype=np.float64))
+        res = E.run_host(plan, pb, self.options, None if V0 is None else np.asarray(V0, dtype=np.float64),
+                         want_ic=True)
         self.last = res
         self._log(res)
+        if res.Ic is not None:  # dev.Ic side channel (:512), read by user scripts (tests/ColpittsCB_Analysis.py:96-101)
+            for q, (_, dev) in enumerate(topo.bjts):
+                dev.Ic = res.Ic[0, q].copy()
         if not res.converged[0]:
             return False, None, None, None, None
         self.freqs = self._freqs(plan)
@@ -125,7 +130,9 @@ class MultiToneHarmonicBalance:
         """Batched parameter sweep.  ``sweeps`` = [(device, field, values[B]), ...]: ``field`` is an attribute the
         reference scripts assign between runs (``ac``, ``dc``, ``phase`` [deg], ``R``, ``C``, ``L``, ``alpha``) or a
         key of ``device.options`` (applied to every device sharing that dict).  ``freq`` (optional [B] or [B][2])
-        sweeps the analysis tone(s); sources and filters at the tone follow it."""
+        sweeps the analysis tone(s); AC sources at a tone follow it (their kind is fixed in the plan), and so does
+        every IdealHarmonicFilter whose ``freq`` equals the nominal tone -- unless the filter's own ``freq`` is
+        swept explicitly."""
         plan, topo = self._setup(netlist)
         B = len(np.asarray(sweeps[0][2])) if sweeps else len(np.asarray(freq))
         pb = ParamBlock(topo, self.freq, B)
@@ -133,19 +140,23 @@ class MultiToneHarmonicBalance:
             pb.set(dev, field, values)
         if freq is not None:
             f = np.asarray(freq, dtype=np.float64)
-            if f.ndim == 1:
-                pb.set_tones(f)
-            else:
-                pb.set_tones(f[:, 0], f[:, 1])
+            swept = {id(dev) for dev, field, _ in sweeps if field == 'freq'}
+            nominal = [self.freq] if topo.num_tones == 1 else list(self.freq)
+            cols = [f] if f.ndim == 1 else [f[:, 0], f[:, 1]]
+            for dev in [d for k, _, d in topo.lin if k == L.LIN_IHF and id(d) not in swept]:
+                for f_nom, col in zip(nominal, cols):
+                    if dev.freq == f_nom:  # the filter's exact-equality test (IdealHarmonicFilter.py:34) must keep hitting
+                        pb.set(dev, 'freq', col)
+            pb.set_tones(*cols)
         return self._run_block(plan, pb, V0)
 
     def _run_block(self, plan, pb, V0):
         self._had_v0 = V0 is not None
         if self.distributed:
             from .._dist import run_block_distributed
-            res = run_block_distributed(plan, pb, self.options, V0)
+            res = run_block_distributed(plan, pb, self.options, V0, levels=self.report_levels)
         else:
-            res = E.run_host(plan, pb, self.options, V0)
+            res = E.run_host(plan, pb, self.options, V0, want_levels=self.report_levels)
         res.freqs = self._freqs(plan)
         if self.num_tones == 2:
             res.freqs = np.abs(res.freqs)

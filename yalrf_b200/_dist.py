@@ -1,65 +1,136 @@
-"""Multi-GPU sharding of a batch: independent circuits are split into contiguous slices, one per rank
-(one process per GPU), solved without any collective inside the Newton loop, and the results are gathered once
-(NCCL over NVLink on the GPU box, gloo in the CPU tests).  SURVEY.md 8e."""
+"""Multi-GPU sharding of a batch: independent circuits are dealt round-robin to the ranks (one process per GPU) --
+circuit b goes to rank b % world, so that neighbouring sweep points, which need similar numbers of Newton
+iterations, spread over all ranks and the ranks finish together -- solved without any collective inside the Newton
+loop, and the results are gathered ONCE: every rank packs its results into one [n][R] fp64 buffer (on the GPU,
+straight from the solver's output buffers) and a single all_gather_into_tensor moves it (NCCL over NVLink on the GPU
+box, gloo in the CPU tests).  SURVEY.md 8e."""
 import numpy as np
 
 from ._engine import BatchResult
 
-_FIELDS = ('V', 'Vf', 'converged', 'newton_iters', 'lu_count', 'level_iters', 'level_alpha', 'err')
+
+def shard_indices(B, rank, world):
+    """global indices of the circuits rank solves: b % world == rank"""
+    return np.arange(rank, B, world)
 
 
-def shard_bounds(B, rank, world):
-    """[lo, hi) of rank's contiguous slice; the first B % world ranks get one extra circuit."""
-    base, rem = divmod(B, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+def shard_count(B, rank, world):
+    return (B - rank + world - 1) // world if B > rank else 0
 
 
-def slice_block(pb, lo, hi):
+def slice_block(pb, idx):
+    """the ParamBlock of the circuits idx (an index array or a slice)"""
     from ._flatten import ParamBlock
     out = ParamBlock.__new__(ParamBlock)
     out.topo = pb.topo
-    out.B = hi - lo
     for name in ('tones', 'lin_val', 'src_val', 'src_ac', 'src_phase', 'diode_par', 'bjt_par', 'cubic_par'):
-        setattr(out, name, np.ascontiguousarray(getattr(pb, name)[lo:hi]))
+        setattr(out, name, np.ascontiguousarray(getattr(pb, name)[idx]))
+    out.B = out.tones.shape[0]
     return out
 
 
-def gather_results(plan, local, B, group=None):
-    """all_gather of the per-rank BatchResults into one BatchResult of the whole batch (on every rank)."""
+class PackLayout:
+    """columns of the packed result row of one circuit (fp64; the int32 reports are exact in fp64)"""
+
+    def __init__(self, plan, levels=True):
+        from . import _lib as L
+        self.fields = [('V', plan.W), ('Vf', plan.N * (plan.K + 1) * 2), ('err', 1), ('converged', 1),
+                       ('newton_iters', 1), ('lu_count', 1)]
+        if levels:
+            self.fields += [('level_iters', L.MAX_LEVELS), ('level_alpha', L.MAX_LEVELS)]
+        self.levels = levels
+        self.off = {}
+        o = 0
+        for name, n in self.fields:
+            self.off[name] = (o, o + n)
+            o += n
+        self.R = o
+
+
+def pack_host(res, lay):
+    """BatchResult (host) -> [n][R] fp64"""
+    out = np.zeros((res.B, lay.R))
+    for name, _ in lay.fields:
+        a = getattr(res, name)
+        if np.iscomplexobj(a):
+            a = np.ascontiguousarray(a).view(np.float64)
+        lo, hi = lay.off[name]
+        out[:, lo:hi] = np.asarray(a, dtype=np.float64).reshape(res.B, -1)
+    return out
+
+
+def pack_device(db, lay):
+    """DeviceBatch (results in HBM) -> [n][R] fp64 cuda tensor, one fused copy kernel per field"""
     import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    nmax = max(shard_bounds(B, r, world)[1] - shard_bounds(B, r, world)[0] for r in range(world))
-    use_cuda = dist.get_backend(group) == 'nccl'
-    full = BatchResult(plan, B)
-    for name in _FIELDS:
-        a = getattr(local, name)
-        isc = np.iscomplexobj(a)
-        if isc:
-            a = a.view(np.float64)
-        pad = np.zeros((nmax,) + a.shape[1:], dtype=a.dtype)
-        pad[:a.shape[0]] = a
-        t = torch.from_numpy(pad)
-        if use_cuda:
-            t = t.cuda()
-        outs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(outs, t, group=group)
+    out = torch.empty((db.B, lay.R), dtype=torch.float64, device=db.dev)
+    for name, _ in lay.fields:
+        lo, hi = lay.off[name]
+        out[:, lo:hi] = getattr(db, name).reshape(db.B, -1)
+    return out
+
+
+def unpack(plan, rows, lay):
+    """[B][R] fp64 (host) -> BatchResult"""
+    B = rows.shape[0]
+    full = BatchResult(plan, B, levels=lay.levels)
+    for name, _ in lay.fields:
+        lo, hi = lay.off[name]
         dst = getattr(full, name)
-        dstv = dst.view(np.float64) if isc else dst
-        for r in range(world):
-            lo, hi = shard_bounds(B, r, world)
-            dstv[lo:hi] = outs[r][:hi - lo].cpu().numpy()
+        if np.iscomplexobj(dst):
+            dst.view(np.float64).reshape(B, -1)[:] = rows[:, lo:hi]
+        else:
+            dst.reshape(B, -1)[:] = rows[:, lo:hi]
     return full
 
 
-def run_block_distributed(plan, pb, options, V0=None, group=None, run_fn=None):
-    """Solve this rank's slice of the block and gather.  run_fn(plan, pb, options, V0) -> BatchResult."""
+def gather_packed(local, B, group=None):
+    """local: this rank's [n][R] rows (numpy, or a cuda tensor with the nccl backend).  Returns the [B][R] rows of the
+    whole batch in circuit order on the host (every rank), from ONE all_gather_into_tensor."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nmax = shard_count(B, 0, world)
+    use_cuda = dist.get_backend(group) == 'nccl'
+    t = torch.from_numpy(np.ascontiguousarray(local)) if isinstance(local, np.ndarray) else local
+    if use_cuda and not t.is_cuda:
+        t = t.cuda()
+    R = t.shape[1]
+    if t.shape[0] < nmax:  # ranks with one circuit less: pad to the common row count
+        t = torch.cat([t, torch.zeros((nmax - t.shape[0], R), dtype=t.dtype, device=t.device)])
+    out = torch.empty((world * nmax, R), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    if use_cuda:
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = host
+    rows = out.numpy().reshape(world, nmax, R)
+    b = np.arange(B)
+    return rows[b % world, b // world]     # circuit b = row b // world of rank b % world
+
+
+def run_block_distributed(plan, pb, options, V0=None, group=None, run_fn=None, levels=True):
+    """Solve this rank's circuits of the block and gather.  run_fn(plan, pb, options, V0) -> BatchResult (host) is
+    for tests; the default keeps parameters and results in HBM (DeviceBatch) and packs / gathers on the device."""
     import torch.distributed as dist
     from . import _engine as E
-    run_fn = run_fn or E.run_host
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    lo, hi = shard_bounds(pb.B, rank, world)
-    v0 = None if V0 is None else np.asarray(V0).reshape(pb.B, -1)[lo:hi]
-    local = run_fn(plan, slice_block(pb, lo, hi), options, v0) if hi > lo else BatchResult(plan, 0)
-    return gather_results(plan, local, pb.B, group)
+    idx = shard_indices(pb.B, rank, world)
+    lay = PackLayout(plan, levels)
+    v0 = None if V0 is None else np.asarray(V0, dtype=np.float64).reshape(pb.B, -1)[idx]
+    if len(idx) == 0:
+        local = np.zeros((0, lay.R))
+    elif run_fn is not None:
+        local = pack_host(run_fn(plan, slice_block(pb, idx), options, v0), lay)
+    else:
+        import torch
+        db = E.DeviceBatch(plan, slice_block(pb, idx), pinned_upload=True)
+        if v0 is not None:
+            db.V.copy_(torch.from_numpy(v0), non_blocking=False)
+        db.solve(options, have_v0=v0 is not None)
+        if v0 is not None and bool((db.converged < 0).any().item()):
+            # a direct attempt failed and needs the DC point (:333-335): rerun from the same V0 with it
+            db.V.copy_(torch.from_numpy(v0))
+            db.solve(options, have_v0=True, with_dc=True)
+        local = pack_device(db, lay)
+    return unpack(plan, gather_packed(local, pb.B, group), lay)

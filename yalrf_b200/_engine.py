@@ -6,7 +6,25 @@ import numpy as np
 from . import _lib as L
 from ._flatten import ParamBlock, Topology, dft_tables, source_kinds
 
-_plans = {}
+from collections import OrderedDict
+
+_plans = OrderedDict()   # (device, topology, flags) -> Plan, least recently used first
+MAX_PLANS = 64           # each plan pins device tables + the staging buffer of its largest batch
+
+
+def clear_plans():
+    """Destroy every cached plan (their device tables and staging buffers are freed)."""
+    _plans.clear()
+
+
+def _current_device():
+    """CUDA device the plan will live on (its tables are device memory); -1 without a GPU -- yhb_plan_create then
+    fails with 'no CPU fallback'."""
+    try:
+        import torch
+        return torch.cuda.current_device() if torch.cuda.is_available() else -1
+    except Exception:
+        return -1
 
 
 class Plan:
@@ -101,11 +119,18 @@ def get_plan(netlist, freq, numharmonics, flags=0, match_tones=True):
                          'of two floats)')
     topo = Topology(netlist, num_tones, nh)
     kinds = source_kinds(topo, freq, match_tones)
-    key = topo.key(kinds, flags)
+    dev = _current_device()
+    key = (dev,) + topo.key(kinds, flags)
     plan = _plans.get(key)
     if plan is None:
+        if dev >= 0:
+            L.check(L.lib().yhb_set_device(dev))
         plan = Plan(topo, kinds, flags)
         _plans[key] = plan
+        while len(_plans) > MAX_PLANS:   # Plan.__del__ calls yhb_plan_destroy once the last user drops it
+            _plans.popitem(last=False)
+    else:
+        _plans.move_to_end(key)
     return plan, topo
 
 
@@ -123,7 +148,7 @@ def _host_array(shape, dtype, pinned, zero=True):
 class BatchResult:
     """Results of a batched solve (numpy, host)."""
 
-    def __init__(self, plan, B, pinned=False):
+    def __init__(self, plan, B, pinned=False, levels=True):
         self.B = B
         # every array is written in full by the D2H copies of yhb_run_host / the gather of _dist: no zero fill
         self.V = _host_array((B, plan.W), np.float64, pinned, zero=False)
@@ -131,11 +156,16 @@ class BatchResult:
         self.converged = _host_array((B,), np.int32, pinned, zero=False)
         self.newton_iters = _host_array((B,), np.int32, pinned, zero=False)
         self.lu_count = _host_array((B,), np.int32, pinned, zero=False)
-        self.level_iters = _host_array((B, L.MAX_LEVELS), np.int32, pinned, zero=False)
-        self.level_alpha = _host_array((B, L.MAX_LEVELS), np.float64, pinned, zero=False)
+        # 'NR number of iterations' / 'Alpha level' of every hb_loop call: 768 B per circuit, optional
+        self.level_iters = _host_array((B, L.MAX_LEVELS), np.int32, pinned, zero=False) if levels else None
+        self.level_alpha = _host_array((B, L.MAX_LEVELS), np.float64, pinned, zero=False) if levels else None
         self.err = _host_array((B,), np.float64, pinned, zero=False)
+        self.Inl = None
+        self.Ic = None
 
     def levels(self, b=0):
+        if self.level_iters is None:
+            raise RuntimeError('per-level reports were not requested (hb.report_levels = False)')
         it = self.level_iters[b]
         return it[it > 0].tolist()
 
@@ -160,11 +190,13 @@ def make_options(options):
     return o
 
 
-def run_host(plan, pb, options, V0=None, want_inl=False):
+def run_host(plan, pb, options, V0=None, want_inl=False, want_levels=True, want_ic=False):
     """run() for a batch through yhb_run_host: host arrays in, host arrays out (H2D / D2H inside)."""
     pb.finalize()
-    res = BatchResult(plan, pb.B, pinned=pb.B >= 256)     # page-locked results for large batches
+    res = BatchResult(plan, pb.B, pinned=pb.B >= 256, levels=want_levels)     # page-locked results for large batches
     res.Inl = np.zeros((pb.B, plan.W)) if want_inl else None
+    nbjt = len(plan.topo.bjts)
+    res.Ic = np.zeros((pb.B, nbjt, plan.S)) if (want_ic and nbjt) else None
     r = L.Result()
     r.V = L.ptr(res.V)
     r.Vf = L.ptr(res.Vf)
@@ -175,6 +207,7 @@ def run_host(plan, pb, options, V0=None, want_inl=False):
     r.level_alpha = L.ptr(res.level_alpha)
     r.err = L.ptr(res.err)
     r.Inl = L.ptr(res.Inl)
+    r.Ic = L.ptr(res.Ic)
     p = make_params(pb)
     o = make_options(options)
     v0 = None
@@ -190,7 +223,7 @@ def run_host(plan, pb, options, V0=None, want_inl=False):
 class DeviceBatch:
     """A parameter block resident in HBM (torch owns the buffers) + result / workspace buffers for repeated solves."""
 
-    def __init__(self, plan, pb):
+    def __init__(self, plan, pb, pinned_upload=True):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError('yalrf_b200 needs a CUDA device: there is no CPU fallback')
@@ -228,13 +261,14 @@ class DeviceBatch:
         r.Inl = None
         self.result = r
 
-    def solve(self, options, have_v0=False, stream=None):
-        """DC points + run() for the whole batch on `stream` (default: torch's current stream); no D2H."""
+    def solve(self, options, have_v0=False, stream=None, with_dc=False):
+        """DC points + run() for the whole batch on `stream` (default: torch's current stream); no D2H.
+        with_dc: also compute the DC points for a warm start (needed when a direct attempt fails, :333-335)."""
         import torch
         lib = L.lib()
         st = (stream or torch.cuda.current_stream()).cuda_stream
         o = make_options(options)
-        if not have_v0:
+        if not have_v0 or with_dc:
             L.check(lib.yhb_dc_solve(self.plan.handle, C.byref(self.params), self.ws.data_ptr(), self.ws_bytes,
                                      self.Vdc.data_ptr(), self.dcinfo.data_ptr(), st))
             self.dc_done = True

@@ -53,9 +53,14 @@ class Options(C.Structure):
 
 
 class Result(C.Structure):
-    _fields_ = [('V', C.c_void_p), ('Vf', C.c_void_p), ('converged', C.c_void_p), ('newton_iters', C.c_void_p),
+    """yhb_result; struct_size is filled in by the constructor (the library refuses a struct without it)"""
+    _fields_ = [('struct_size', C.c_size_t), ('V', C.c_void_p), ('Vf', C.c_void_p), ('converged', C.c_void_p), ('newton_iters', C.c_void_p),
                 ('lu_count', C.c_void_p), ('level_iters', C.c_void_p), ('level_alpha', C.c_void_p),
-                ('err', C.c_void_p), ('Inl', C.c_void_p)]
+                ('err', C.c_void_p), ('Inl', C.c_void_p), ('Ic', C.c_void_p)]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.struct_size = C.sizeof(Result)
 
 
 _lib = None

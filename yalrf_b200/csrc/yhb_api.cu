@@ -150,6 +150,20 @@ struct TermList {
     }
 };
 
+// Caller's yhb_result -> a full-size copy: only struct_size bytes are read, later fields are NULL.
+static int load_result(const yhb_result *in, yhb_result &out) {
+    memset(&out, 0, sizeof(out));
+    if (!in) { set_error("null result"); return -1; }
+    const size_t n = in->struct_size;
+    if (n < sizeof(size_t) + sizeof(void *) || n > 4096 || (n % sizeof(void *)) != 0) {
+        set_error("yhb_result.struct_size not set (must be sizeof(yhb_result) of the header the caller was built with)");
+        return -1;
+    }
+    memcpy(&out, in, std::min(n, sizeof(out)));
+    out.struct_size = sizeof(out);
+    return 0;
+}
+
 }  // namespace yhb
 
 using namespace yhb;
@@ -342,6 +356,34 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
         set_error("node index out of range");
         delete pl;
         return -1;
+    }
+    auto check_range = [&](const int32_t *a, int cnt, int lo, int hi) {
+        for (int i = 0; i < cnt; ++i)
+            if (a[i] < lo || a[i] > hi) return false;
+        return true;
+    };
+    if ((d.nlin && !desc->lin_kind) || (d.nsrc && !desc->src_kind) ||
+        !check_range(desc->lin_kind, d.nlin, YHB_LIN_RESISTOR, YHB_LIN_IHF) ||
+        !check_range(desc->src_kind, d.nsrc, YHB_SRC_DC, YHB_SRC_DC_ONLY)) {
+        set_error("linear element / source kind out of range");
+        delete pl;
+        return -1;
+    }
+    if (desc->nl_kind && desc->nl_index) {
+        const int cnt[3] = {d.nd, d.nb, d.nc};
+        std::vector<char> seen[3];
+        for (int k = 0; k < 3; ++k) seen[k].assign(cnt[k], 0);
+        bool okk = true;
+        for (int t = 0; okk && t < d.nd + d.nb + d.nc; ++t) {
+            const int k = desc->nl_kind[t], i = desc->nl_index[t];
+            okk = k >= 0 && k <= 2 && i >= 0 && i < cnt[k] && !seen[k][i];
+            if (okk) seen[k][i] = 1;
+        }
+        if (!okk) {
+            set_error("nl_kind / nl_index must list every nonlinear device exactly once");
+            delete pl;
+            return -1;
+        }
     }
     pl->lin_kind.assign(desc->lin_kind, desc->lin_kind + d.nlin);
     pl->lin_nodes.assign(desc->lin_nodes, desc->lin_nodes + 4 * d.nlin);
@@ -914,6 +956,7 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.rhs = c.take<double>(L.fused ? 1 : (size_t)B * (d.Wc + 1));
     ws.pairwav = c.take<double>((size_t)B * std::max(d.npair_nl, 1) * 2 * S);
     ws.Inl = nullptr;
+    ws.Ic = nullptr;
     ws.list[0] = c.take<int>(B);
     ws.list[1] = c.take<int>(B);
     ws.count = c.take<int>(4);
@@ -978,12 +1021,10 @@ int eval_smem_bytes(const yhb_plan *pl, const Layout &L) {
     return L.eval_smem ? (int)(eval_scratch_doubles(pl->d) * sizeof(double)) : 0;
 }
 
+// the attribute is per device: set it on every call (cheap), like the fused launcher does
 int ensure_eval_attr(int bytes) {
-    static int configured = 0;
-    if (bytes > configured) {
+    if (bytes > 48 * 1024)
         YHB_CUDA(cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxEvalSmem));
-        configured = (int)kMaxEvalSmem;
-    }
     return 0;
 }
 
@@ -1215,47 +1256,59 @@ extern "C" int yhb_dc_solve(const yhb_plan *pl, const yhb_params *p, void *wsbuf
     return 0;
 }
 
+// lock = false: the caller (yhb_run_host) already holds pl->mu
 static int solve_common(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
                         size_t ws_bytes, int have_v0, const double *Vdc, const double *alpha,
-                        const yhb_result *res, void *stream) {
+                        const yhb_result *res_in, void *stream, bool lock) {
     if (int rc = check_params(pl, p)) return rc;
-    if (!res) { set_error("null result"); return -1; }
+    yhb_result R;
+    if (int rc = load_result(res_in, R)) return rc;
     Layout L = carve(pl, p->batch, wsbuf);
     if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
-    if (have_v0 && !res->V) { set_error("have_v0 set but res->V is null"); return -1; }
+    if (have_v0 && !R.V) { set_error("have_v0 set but res->V is null"); return -1; }
     if (!have_v0 && !Vdc) { set_error("cold start needs Vdc"); return -1; }
-    if (res->V) L.ws.V = res->V;
-    L.ws.Inl = res->Inl;
+    if (R.V) L.ws.V = R.V;
+    L.ws.Inl = R.Inl;
+    L.ws.Ic = R.Ic;
     if (Vdc) L.ws.dcV = const_cast<double *>(Vdc);
     L.ws.dc_valid = Vdc != nullptr;
-    std::lock_guard<std::mutex> lk(const_cast<yhb_plan *>(pl)->mu);  // pinned counter buffer is per plan
-    return run_loop(pl, p, opt, L, have_v0, alpha, res, (cudaStream_t)stream);
+    std::unique_lock<std::mutex> lk(const_cast<yhb_plan *>(pl)->mu, std::defer_lock);  // pinned counters are per plan
+    if (lock) lk.lock();
+    return run_loop(pl, p, opt, L, have_v0, alpha, &R, (cudaStream_t)stream);
 }
 
 extern "C" int yhb_solve(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
                          size_t ws_bytes, int32_t have_v0, const double *Vdc, const yhb_result *res, void *stream) {
-    return solve_common(pl, p, opt, wsbuf, ws_bytes, have_v0, Vdc, nullptr, res, stream);
+    return solve_common(pl, p, opt, wsbuf, ws_bytes, have_v0, Vdc, nullptr, res, stream, true);
 }
 
 extern "C" int yhb_newton(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
                           size_t ws_bytes, const double *alpha, const yhb_result *res, void *stream) {
     if (!alpha) { set_error("null alpha"); return -1; }
-    return solve_common(pl, p, opt, wsbuf, ws_bytes, 1, nullptr, alpha, res, stream);
+    return solve_common(pl, p, opt, wsbuf, ws_bytes, 1, nullptr, alpha, res, stream, true);
 }
 
 // ---- end-to-end entry with host buffers -----------------------------------------------------------
-extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb_options *opt, const double *V0,
-                            const yhb_result *hr) {
-    yhb_plan *pl = const_cast<yhb_plan *>(cpl);
-    if (int rc = check_params(pl, hp)) return rc;
-    if (!hr) { set_error("null result"); return -1; }
+// Device staging of a *_host call: parameters + results + workspace in ONE allocation cached on the plan (grown on
+// demand).  The caller holds pl->mu for as long as it uses the buffer and the plan's stream.
+namespace {
+struct HostStage {
+    yhb_params dp;
+    yhb_result dr;
+    void *wsb;
+    size_t wsbytes;
+};
+
+int stage_host(yhb_plan *pl, size_t B, const yhb_result &want, HostStage &hs) {
     const PlanDev &d = pl->d;
-    const size_t B = hp->batch, W = d.W, K1 = d.K + 1;
+    const size_t W = d.W, K1 = d.K + 1;
     if (!pl->own_stream) YHB_CUDA(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
-    cudaStream_t st = pl->own_stream;
-    // device staging: parameters + results + workspace, one allocation cached on the plan
-    Carver c{nullptr, 0};
-    auto plan_bytes = [&](Carver &cv, yhb_params &dp, yhb_result &dr, void *&wsb, size_t wsbytes) {
+    hs.wsbytes = yhb_workspace_bytes(pl, (int)B);
+    auto plan_bytes = [&](Carver &cv) {
+        yhb_params &dp = hs.dp;
+        yhb_result &dr = hs.dr;
+        memset(&dr, 0, sizeof(dr));
+        dr.struct_size = sizeof(dr);
         dp.batch = (int)B;
         dp.tones = cv.take<double>(B * 2);
         dp.lin_val = cv.take<double>(B * std::max(d.nlin, 1) * 2);
@@ -1268,17 +1321,16 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
         dr.converged = cv.take<int32_t>(B);
         dr.newton_iters = cv.take<int32_t>(B);
         dr.lu_count = cv.take<int32_t>(B);
-        dr.level_iters = cv.take<int32_t>(B * YHB_MAX_LEVELS);
-        dr.level_alpha = cv.take<double>(B * YHB_MAX_LEVELS);
+        // the per-level reports are 768 B per circuit: staged (and copied back) only when the caller asks for them
+        dr.level_iters = want.level_iters ? cv.take<int32_t>(B * YHB_MAX_LEVELS) : nullptr;
+        dr.level_alpha = want.level_alpha ? cv.take<double>(B * YHB_MAX_LEVELS) : nullptr;
         dr.err = cv.take<double>(B);
-        dr.Inl = hr->Inl ? cv.take<double>(B * W) : nullptr;
-        wsb = cv.take<char>(wsbytes);
+        dr.Inl = want.Inl ? cv.take<double>(B * W) : nullptr;
+        dr.Ic = want.Ic ? cv.take<double>(B * std::max(d.nb, 1) * d.S) : nullptr;
+        hs.wsb = cv.take<char>(hs.wsbytes);
     };
-    const size_t wsbytes = yhb_workspace_bytes(pl, (int)B);
-    yhb_params dp;
-    yhb_result dr;
-    void *wsb;
-    plan_bytes(c, dp, dr, wsb, wsbytes);
+    Carver c{nullptr, 0};
+    plan_bytes(c);
     const size_t need = align_up(c.off);
     if (need > pl->hbuf_bytes) {
         if (pl->hbuf) cudaFree(pl->hbuf);
@@ -1288,7 +1340,13 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
         pl->hbuf_bytes = need;
     }
     Carver c2{reinterpret_cast<char *>(pl->hbuf), 0};
-    plan_bytes(c2, dp, dr, wsb, wsbytes);
+    plan_bytes(c2);
+    return 0;
+}
+
+int h2d_params(const yhb_plan *pl, const yhb_params *hp, const yhb_params &dp, cudaStream_t st) {
+    const PlanDev &d = pl->d;
+    const size_t B = hp->batch;
 #define H2D(dst, src, cnt)                                                                                   \
     do {                                                                                                     \
         if ((cnt) > 0 && (src))                                                                              \
@@ -1300,16 +1358,59 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
     H2D(dp.diode_par, hp->diode_par, B * d.nd * YHB_DIODE_NPAR);
     H2D(dp.bjt_par, hp->bjt_par, B * d.nb * YHB_BJT_NPAR);
     H2D(dp.cubic_par, hp->cubic_par, B * d.nc);
-    if (V0) H2D(dr.V, V0, B * W);
 #undef H2D
+    return 0;
+}
+
+int d2h_result(const yhb_plan *pl, size_t B, const yhb_result &hr, const yhb_result &dr, cudaStream_t st) {
+    const PlanDev &d = pl->d;
+    const size_t W = d.W, K1 = d.K + 1;
+#define D2H(dst, src, cnt)                                                                              \
+    do {                                                                                                \
+        if ((dst) && (src)) YHB_CUDA(cudaMemcpyAsync((dst), (src), (cnt) * sizeof(*(dst)), cudaMemcpyDeviceToHost, st)); \
+    } while (0)
+    D2H(hr.V, dr.V, B * W);
+    D2H(hr.Vf, dr.Vf, B * d.N * K1 * 2);
+    D2H(hr.converged, dr.converged, B);
+    D2H(hr.newton_iters, dr.newton_iters, B);
+    D2H(hr.lu_count, dr.lu_count, B);
+    D2H(hr.level_iters, dr.level_iters, B * YHB_MAX_LEVELS);
+    D2H(hr.level_alpha, dr.level_alpha, B * YHB_MAX_LEVELS);
+    D2H(hr.err, dr.err, B);
+    D2H(hr.Inl, dr.Inl, B * W);
+    D2H(hr.Ic, dr.Ic, B * d.nb * d.S);
+#undef D2H
+    return 0;
+}
+}  // namespace
+
+extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb_options *opt, const double *V0,
+                            const yhb_result *hr_in) {
+    yhb_plan *pl = const_cast<yhb_plan *>(cpl);
+    if (int rc = check_params(pl, hp)) return rc;
+    yhb_result hr;
+    if (int rc = load_result(hr_in, hr)) return rc;
+    // the staging buffer, the stream and the pinned counters belong to the plan: one host call at a time per plan
+    std::lock_guard<std::mutex> lk(pl->mu);
+    const PlanDev &d = pl->d;
+    const size_t B = hp->batch, W = d.W;
+    HostStage hs;
+    if (int rc = stage_host(pl, B, hr, hs)) return rc;
+    cudaStream_t st = pl->own_stream;
+    yhb_params &dp = hs.dp;
+    yhb_result &dr = hs.dr;
+    void *wsb = hs.wsb;
+    const size_t wsbytes = hs.wsbytes;
+    if (int rc = h2d_params(pl, hp, dp, st)) return rc;
+    if (V0) YHB_CUDA(cudaMemcpyAsync(dr.V, V0, B * W * sizeof(double), cudaMemcpyHostToDevice, st));
     Layout L = carve(pl, (int)B, wsb);
     if (!V0) {  // cold start: DC operating points first (calc_V0, :321-322)
         if (int rc = yhb_dc_solve(pl, &dp, wsb, wsbytes, nullptr, nullptr, st)) return rc;
-        if (int rc = yhb_solve(pl, &dp, opt, wsb, wsbytes, 0, L.ws.dcV, &dr, st)) return rc;
+        if (int rc = solve_common(pl, &dp, opt, wsb, wsbytes, 0, L.ws.dcV, nullptr, &dr, st, false)) return rc;
     } else {
         // warm start: the DC analysis is only needed if a direct attempt fails (:333-335); such circuits come
         // back with converged = -1 and the batch is re-run from the same V0 with the DC points available
-        if (int rc = yhb_solve(pl, &dp, opt, wsb, wsbytes, 1, nullptr, &dr, st)) return rc;
+        if (int rc = solve_common(pl, &dp, opt, wsb, wsbytes, 1, nullptr, nullptr, &dr, st, false)) return rc;
         std::vector<int32_t> conv(B);
         YHB_CUDA(cudaMemcpyAsync(conv.data(), dr.converged, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         YHB_CUDA(cudaStreamSynchronize(st));
@@ -1318,23 +1419,10 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
         if (need_dc) {
             YHB_CUDA(cudaMemcpyAsync(dr.V, V0, B * W * sizeof(double), cudaMemcpyHostToDevice, st));
             if (int rc = yhb_dc_solve(pl, &dp, wsb, wsbytes, nullptr, nullptr, st)) return rc;
-            if (int rc = yhb_solve(pl, &dp, opt, wsb, wsbytes, 1, L.ws.dcV, &dr, st)) return rc;
+            if (int rc = solve_common(pl, &dp, opt, wsb, wsbytes, 1, L.ws.dcV, nullptr, &dr, st, false)) return rc;
         }
     }
-#define D2H(dst, src, cnt)                                                                              \
-    do {                                                                                                \
-        if (dst) YHB_CUDA(cudaMemcpyAsync((dst), (src), (cnt) * sizeof(*(dst)), cudaMemcpyDeviceToHost, st)); \
-    } while (0)
-    D2H(hr->V, dr.V, B * W);
-    D2H(hr->Vf, dr.Vf, B * d.N * K1 * 2);
-    D2H(hr->converged, dr.converged, B);
-    D2H(hr->newton_iters, dr.newton_iters, B);
-    D2H(hr->lu_count, dr.lu_count, B);
-    D2H(hr->level_iters, dr.level_iters, B * YHB_MAX_LEVELS);
-    D2H(hr->level_alpha, dr.level_alpha, B * YHB_MAX_LEVELS);
-    D2H(hr->err, dr.err, B);
-    D2H(hr->Inl, dr.Inl, B * W);
-#undef D2H
+    if (int rc = d2h_result(pl, B, hr, dr, st)) return rc;
     YHB_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

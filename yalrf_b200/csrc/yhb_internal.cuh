@@ -158,6 +158,7 @@ struct Workspace {
     double *J;           // staged engine: core Jacobians [B][j_stride] (stage entry point: caller's full [B][W][W])
     size_t j_stride;
     double *Inl;         // [B][W] optional output: nonlinear current spectrum of the last evaluation (or nullptr)
+    double *Ic;          // [B][nb][S] optional output: collector-current samples of the last evaluation (:512)
     double *pairwav;     // [B][npair_nl][2][S] pair conductance / capacitance waveforms (staged engine)
     double *xstep;       // [B][x_stride]  staged engine: Newton step vector + scratch of newton_pre / newton_post
     size_t x_stride;
