@@ -191,6 +191,11 @@ int yhb_plan_engine(const yhb_plan *plan);
  * factored concurrently), 0 = dense Gauss-Jordan of the whole core; *doubles (optional) = size of the block-row
  * storage in doubles */
 int yhb_plan_block_sparse(const yhb_plan *plan, int32_t *doubles);
+/* floating-point operations of ONE Newton-step linear solve: *lu_reference = the W x W dgetrf + dgetrs the reference
+ * runs (:620-621, SURVEY 8d: 2/3 W^3 + 2 W^2), *lu_core_dense = the same for the Wc x Wc core left after peeling,
+ * *lu_executed = what the engine chosen for this plan really executes (block-sparse LU over node blocks, tensor-core
+ * Gauss-Jordan, banded or block-Thomas elimination).  Any pointer may be NULL. */
+int yhb_plan_flops(const yhb_plan *plan, double *lu_reference, double *lu_core_dense, double *lu_executed);
 /* real frequency of each bin of circuit tones (f1, f2), as self.freqs (:251, :271): host helper */
 int yhb_plan_freqs(const yhb_plan *plan, double f1, double f2, double *freqs /* [K+1] */);
 
@@ -237,6 +242,10 @@ int yhb_stage_assemble(const yhb_plan *plan, const yhb_params *p, void *ws, size
 /* the fused engine's register-tiled Gauss-Jordan solver on its own: x[B][n] = A^-1 b, A[B][n][n] row-major,
  * 1 <= n <= 127 */
 int yhb_stage_gj(int32_t batch, int32_t n, const double *A, const double *b, double *x, void *stream);
+/* the staged engines' panel Gauss-Jordan solver (16 pivot columns per panel, DMMA trailing updates; the core solve of
+ * large dense cores and of the block rows of the block-Thomas engine) on its own: X[B][n][nrhs] = A^-1 Bm,
+ * A[B][n][n] and Bm[B][n][nrhs] row-major.  Synchronises the stream (it owns temporary device memory). */
+int yhb_stage_gjp(int32_t batch, int32_t n, int32_t nrhs, const double *A, const double *Bm, double *X, void *stream);
 /* LU with partial pivoting + solve (:620-621): x[B][W] = J^-1 F; J is overwritten by its factors */
 int yhb_stage_lu(int32_t batch, int32_t W, double *J, const double *F, double *x, void *stream);
 

@@ -206,3 +206,45 @@ def test_stage_gj_random():
         ref = np.linalg.solve(A, b[:, :, None])[:, :, 0]
         for k in range(B):
             assert relmax(x.cpu().numpy()[k], ref[k]) < 1e-9 * max(1.0, np.linalg.cond(A[k]) * 1e-4), (n, k)
+
+
+def test_stage_gjp_random():
+    """The staged engines' panel Gauss-Jordan solver (k_gjp_panel + DMMA k_gjp_update, yhb_dense.cuh) against LAPACK:
+    sizes around the panel width and the 8-row tiles, the config-3 core (289) and a config-5 block row (1089 pivots
+    with carried columns), wild row scaling, zero diagonals, several right-hand sides."""
+    import torch
+    from yalrf_b200 import _lib as L
+    rng = np.random.default_rng(7)
+    for n, nrhs, B in [(1, 1, 2), (5, 1, 3), (15, 2, 3), (16, 1, 3), (17, 3, 3), (33, 1, 3), (100, 5, 3), (289, 1, 4),
+                       (300, 40, 2), (1089, 1090, 1)]:
+        A = rng.normal(size=(B, n, n))
+        if B > 1:
+            A[1] *= np.exp(rng.uniform(-20, 20, size=(n, 1)))      # wild row scaling
+        if B > 2 and n > 2:
+            A[2][np.arange(n), np.arange(n)] = 0.0                  # zero diagonal: pivoting is mandatory
+        b = rng.normal(size=(B, n, nrhs))
+        x = torch.zeros((B, n, nrhs), dtype=torch.float64, device='cuda')
+        dA, db = _dev(A), _dev(b)
+        L.check(L.lib().yhb_stage_gjp(B, n, nrhs, dA.data_ptr(), db.data_ptr(), x.data_ptr(), None))
+        torch.cuda.synchronize()
+        ref = np.linalg.solve(A, b)
+        for k in range(B):
+            assert relmax(x.cpu().numpy()[k], ref[k]) < 1e-9 * max(1.0, np.linalg.cond(A[k]) * 1e-4), (n, nrhs, k)
+
+
+def test_stage_gjp_singular_reports_nan():
+    """a column without an admissible pivot (all NaN) flags the system: the solution is NaN (the Newton loop's NaN
+    guard takes it from there, :624-627), the other systems of the batch are unaffected"""
+    import torch
+    from yalrf_b200 import _lib as L
+    rng = np.random.default_rng(8)
+    n = 40
+    A = rng.normal(size=(2, n, n))
+    A[0][:, 7] = np.nan
+    b = rng.normal(size=(2, n, 1))
+    x = torch.zeros((2, n, 1), dtype=torch.float64, device='cuda')
+    dA, db = _dev(A), _dev(b)
+    L.check(L.lib().yhb_stage_gjp(2, n, 1, dA.data_ptr(), db.data_ptr(), x.data_ptr(), None))
+    xs = x.cpu().numpy()
+    assert np.isnan(xs[0]).all()
+    assert relmax(xs[1], np.linalg.solve(A[1], b[1])) < 1e-9

@@ -94,6 +94,12 @@ class Plan:
         """levels of the fused engine's block-sparse LU over node blocks (0 = dense Gauss-Jordan of the core)"""
         return int(L.lib().yhb_plan_block_sparse(self.handle, None))
 
+    def flops(self):
+        """(reference, dense core, executed) floating-point operations of one Newton-step linear solve"""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        L.check(L.lib().yhb_plan_flops(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def freqs(self, f1, f2=0.0):
         out = np.zeros(self.K + 1)
         L.check(L.lib().yhb_plan_freqs(self.handle, float(f1), float(f2), out.ctypes.data_as(C.POINTER(C.c_double))))

@@ -69,8 +69,8 @@ PROF_KINDS = ['prepare', 'dc', 'init', 'eval', 'assemble', 'lu', 'finish', 'fuse
 
 EXPORTS = ['yhb_last_error', 'yhb_version', 'yhb_set_device', 'yhb_profile_enable', 'yhb_profile_reset',
            'yhb_profile_read', 'yhb_fp64_peak', 'yhb_plan_create', 'yhb_plan_destroy',
-           'yhb_plan_dims', 'yhb_plan_core', 'yhb_plan_band', 'yhb_plan_engine', 'yhb_plan_block_sparse', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_newton',
-           'yhb_run_host', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu', 'yhb_stage_gj', 'yhb_debug_timing']
+           'yhb_plan_dims', 'yhb_plan_core', 'yhb_plan_band', 'yhb_plan_engine', 'yhb_plan_block_sparse', 'yhb_plan_flops', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_newton',
+           'yhb_run_host', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu', 'yhb_stage_gj', 'yhb_stage_gjp', 'yhb_debug_timing']
 
 
 def lib():
@@ -96,6 +96,7 @@ def lib():
     L.yhb_plan_band.argtypes = [C.c_void_p]
     L.yhb_plan_engine.argtypes = [C.c_void_p]
     L.yhb_plan_block_sparse.argtypes = [C.c_void_p, _i32p]
+    L.yhb_plan_flops.argtypes = [C.c_void_p, _f64p, _f64p, _f64p]
     L.yhb_plan_freqs.argtypes = [C.c_void_p, C.c_double, C.c_double, _f64p]
     L.yhb_workspace_bytes.argtypes = [C.c_void_p, C.c_int32]
     L.yhb_workspace_bytes.restype = C.c_size_t
@@ -112,6 +113,7 @@ def lib():
     L.yhb_stage_assemble.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.yhb_stage_gj.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.yhb_stage_gjp.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.yhb_stage_lu.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.yhb_debug_timing.argtypes = [C.POINTER(C.c_ulonglong), C.c_int32]
     _lib = L

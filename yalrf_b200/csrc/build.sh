@@ -6,6 +6,5 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="${YHB_OUT:-$HERE/../libyhb.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a \
-    -Xcompiler -fPIC,-O2,-Wall -shared -o "$OUT" "$HERE/yhb_api.cu" -lcublas -lcusolver \
-    -Xlinker -rpath=/usr/local/cuda/lib64 "$@"
+    -Xcompiler -fPIC,-O2,-Wall -shared -o "$OUT" "$HERE/yhb_api.cu" "$@"
 echo "built $OUT"

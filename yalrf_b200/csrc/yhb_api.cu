@@ -1,9 +1,7 @@
 // libyhb.so -- C ABI (include/yhb.h) over the staged harmonic-balance kernels.
 // Host side: plan compilation (stamp tables), workspace carving, and the launch loop that plays
 // run() / hb_loop (yalrf/Analyses/MultiToneHarmonicBalance.py:234-631) for a whole batch.
-#include <cublas_v2.h>
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -17,6 +15,7 @@
 #include <vector>
 
 #include "yhb_dc.cuh"
+#include "yhb_dense.cuh"
 #include "yhb_kernels.cuh"
 
 namespace yhb {
@@ -46,6 +45,13 @@ constexpr size_t kMaxEvalSmem = 200 * 1024;
 
 // instantiated tile counts of the fused engine (a core of Wc unknowns needs Wc + 1 <= 8 NT)
 #define YHB_FOR_NT(X) X(3) X(6) X(8) X(11) X(16)
+
+// block-Thomas engine (block Gauss-Jordan of [D_i | U_i | b_i] + Schur complements), multiply-adds x 2 per core solve:
+// per block row S pivots x S rows x (columns right of the pivot in D_i + S of U_i + 1), then D_{i+1} -= L U' (S^3)
+static double btd_flops(const PlanDev &d) {
+    const double S = d.S, Nc = d.Nc;
+    return Nc * (2.0 * S * S * (0.5 * S + S + 1)) + (Nc - 1) * (2.0 * S * S * S + 2.0 * S * S) + (Nc - 1) * 2.0 * S * S;
+}
 
 // which fused-engine variant runs this plan (if any)
 static FusedChoice fused_choice(const PlanDev &d) {
@@ -180,13 +186,7 @@ struct yhb_plan : public yhb::Plan {
     void *hbuf;
     size_t hbuf_bytes;
     std::mutex mu;
-    // block-Thomas engine: library handles and scratch, created on first use
-    cublasHandle_t blas;
-    cusolverDnHandle_t solver;
-    double *btd_work;
-    int btd_lwork;
-    int *btd_ipiv, *btd_info;
-    std::vector<int> btd_list;
+    std::vector<int> bs_host;  // block-sparse structure per core node: nlater, block rows below, 0, 0 (yhb_plan_flops)
 };
 
 extern "C" const char *yhb_last_error(void) { return g_err.c_str(); }
@@ -700,6 +700,13 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
             d.bs_zero = nnz1 != nnz0;  // fill blocks hold no pair: only then the storage needs zeroing before assembly
         }
     }
+    if (d.bs_ok)
+        for (int k = 0; k < d.Nc; ++k) {
+            pl->bs_host.push_back(bs_nlater[k]);
+            pl->bs_host.push_back(bs_below_ptr[k + 1] - bs_below_ptr[k]);
+            pl->bs_host.push_back(0);
+            pl->bs_host.push_back(0);
+        }
     d.nA = (int)a_row.size();
     d.nB = (int)b_row.size();
     std::vector<int> a_ptr(1, 0), a_pair, a_m, b_ptr(1, 0), b_pair, b_m, r_ptr(1, 0), r_pair, r_m;
@@ -822,12 +829,6 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     pl->nl_index_dev = upload(pl, pl->nl_index);
     ok = ok && pl->lin_nodes_dev && pl->nl_kind_dev && pl->nl_index_dev;
     pl->pinned_counts = nullptr;
-    pl->blas = nullptr;
-    pl->solver = nullptr;
-    pl->btd_work = nullptr;
-    pl->btd_lwork = 0;
-    pl->btd_ipiv = nullptr;
-    pl->btd_info = nullptr;
     pl->own_stream = nullptr;
     pl->hbuf = nullptr;
     pl->hbuf_bytes = 0;
@@ -846,11 +847,6 @@ extern "C" void yhb_plan_destroy(yhb_plan *pl) {
     for (void *p : pl->allocs) cudaFree(p);
     if (pl->pinned_counts) cudaFreeHost(pl->pinned_counts);
     if (pl->hbuf) cudaFree(pl->hbuf);
-    if (pl->btd_work) cudaFree(pl->btd_work);
-    if (pl->btd_ipiv) cudaFree(pl->btd_ipiv);
-    if (pl->btd_info) cudaFree(pl->btd_info);
-    if (pl->blas) cublasDestroy(pl->blas);
-    if (pl->solver) cusolverDnDestroy(pl->solver);
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
     delete pl;
 }
@@ -878,6 +874,49 @@ extern "C" int yhb_plan_block_sparse(const yhb_plan *pl, int32_t *doubles) {
     const bool on = pl->d.bs_ok && fused_choice(pl->d).ok;
     if (doubles) *doubles = on ? pl->d.bs_total : 0;
     return on ? pl->d.bs_nlev : 0;
+}
+
+namespace { int gjp_pivots(const PlanDev &d); }
+// Floating-point operations of ONE Newton-step linear solve: what the reference hands to LAPACK, a dense
+// factorisation of the peeled core, and what the engine chosen for this plan really executes (multiply-adds x 2 of the
+// factorisation + substitution loops; transforms, assembly and device evaluation are not counted).
+extern "C" int yhb_plan_flops(const yhb_plan *pl, double *lu_reference, double *lu_core_dense, double *lu_executed) {
+    if (!pl) { set_error("null plan"); return -1; }
+    const PlanDev &d = pl->d;
+    const double W = d.W, Wc = d.Wc, S = d.S;
+    if (lu_reference) *lu_reference = (2.0 / 3.0) * W * W * W + 2.0 * W * W;  // dgetrf + dgetrs of W x W
+    if (lu_core_dense) *lu_core_dense = (2.0 / 3.0) * Wc * Wc * Wc + 2.0 * Wc * Wc;
+    if (!lu_executed) return 0;
+    const FusedChoice fc = fused_choice(d);
+    double ex = 0.;
+    if (fc.ok && d.bs_ok && pl->bs_host.size() == (size_t)4 * d.Nc) {
+        // bs_factor_row: S pivots, S - 1 other rows, columns right of the pivot up to nact; bs_schur: S multiply-adds
+        // per updated element; bs_back: S per later block and row
+        for (int k = 0; k < d.Nc; ++k) {
+            const double nlater = pl->bs_host[4 * k], nbelow = pl->bs_host[4 * k + 1];
+            const double nact = S * (1 + nlater) + 1;
+            for (int c = 0; c < d.S; ++c) ex += 2.0 * (S - 1) * (nact - c - 1);
+            ex += (nact - S) * S;                                // rows scaled to unit pivots
+            ex += 2.0 * nbelow * S * (S * nlater + 1) * S;       // Schur updates of the block rows below
+            ex += 2.0 * nlater * S * S;                          // back substitution
+        }
+    } else if (fc.ok && fc.NT > 0) {
+        // gj_solve_mma: per 4-column panel, every tile column right of (and including) the owner gets a rank-4 update
+        // over all NT row tiles (8 x 8 x 4 multiply-adds each) + the panel factorisation in registers
+        const int NT = fc.NT, npanel = (d.Wc + 3) / 4;
+        for (int kp = 0; kp < npanel; ++kp) ex += 2.0 * (NT - (kp >> 1)) * NT * 256.0 + 2.0 * 8 * NT * 6;
+    } else if (d.btd) {
+        ex = btd_flops(d);
+    } else if (gjp_pivots(d) > 0) {
+        ex = Wc * Wc * Wc + 2.0 * Wc * Wc;  // panel Gauss-Jordan: full-height rank-16 updates of the columns right of the panel
+    } else if (d.band > 0) {
+        const double kl = d.band;
+        ex = Wc * (2.0 * kl * (2 * kl + 1) + 4.0 * kl);
+    } else {
+        ex = (2.0 / 3.0) * Wc * Wc * Wc + 2.0 * Wc * Wc;
+    }
+    *lu_executed = ex;
+    return 0;
 }
 
 extern "C" int yhb_plan_core(const yhb_plan *pl, int32_t *Nc, int32_t *Wc, int32_t *fused) {
@@ -910,6 +949,16 @@ struct Carver {
     }
 };
 
+
+// pivots per system of the panel Gauss-Jordan solver for this plan's staged engine: S for the block rows of the
+// block-Thomas engine, Wc for a dense core large enough to be worth the per-panel launches, 0 = one-CTA elimination
+constexpr int kGjpMinCore = 128;
+int gjp_pivots(const PlanDev &d) {
+    if (d.btd) return d.S;
+    if (d.band > 0 || d.Wc < kGjpMinCore) return 0;
+    return d.Wc;
+}
+int gjp_dense_ld(int Wc) { return (Wc + 2) & ~1; }  // [J | rhs | pad]: even and > Wc
 
 struct Layout {
     Workspace ws;
@@ -947,14 +996,24 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.scratch = c.take<double>(L.eval_smem ? 1 : (size_t)B * esd);
     L.fc = fused_choice(d);
     L.fused = L.fc.ok;
+    const int gjn = L.fused ? 0 : gjp_pivots(d);
     ws.j_stride = L.fused ? 0
-                  : d.btd ? (size_t)3 * d.Nc * d.S * d.S
-                          : (d.band > 0 ? (size_t)d.Wc * band_ld(d.band) : (size_t)d.Wc * d.Wc);
+                  : d.btd ? (size_t)d.Nc * btd_row_doubles(d.S)
+                          : (d.band > 0 ? (size_t)d.Wc * band_ld(d.band)
+                                        : (size_t)d.Wc * (gjn ? gjp_dense_ld(d.Wc) : d.Wc));
     ws.J = c.take<double>(L.fused ? 1 : (size_t)B * ws.j_stride);
     ws.x_stride = W + newton_scratch_doubles(d);
     ws.xstep = c.take<double>(L.fused ? 1 : B * ws.x_stride);
     ws.rhs = c.take<double>(L.fused ? 1 : (size_t)B * (d.Wc + 1));
     ws.pairwav = c.take<double>((size_t)B * std::max(d.npair_nl, 1) * 2 * S);
+    ws.gj_n = gjn;
+    ws.gj_lpad = (gjn + 7) & ~7;
+    ws.gj_L = c.take<double>(gjn ? (size_t)B * kGjpNB * ws.gj_lpad : 1);
+    ws.gj_piv = c.take<double>(gjn ? (size_t)B * gjn : 1);
+    ws.gj_rowof = c.take<int>(gjn ? (size_t)B * gjn : 1);
+    ws.gj_used = c.take<int>(gjn ? (size_t)B * gjn : 1);
+    ws.gj_pp = c.take<int>((size_t)B * kGjpNB);
+    ws.gj_fail = c.take<int>(B);
     ws.Inl = nullptr;
     ws.Ic = nullptr;
     ws.list[0] = c.take<int>(B);
@@ -1045,61 +1104,102 @@ int launch_finish(const yhb_plan *pl, Layout &L, const yhb_result *res, cudaStre
     return 0;
 }
 
-// Block-Thomas elimination of one circuit's block-tridiagonal core (blocks as k_assemble_btd laid them out), right-hand
-// side / solution in rhs[Wc]:
-//   forward, block row i:  D_i -= L_i U'_{i-1},  b_i -= L_i b'_{i-1};  D_i = P L U (partial pivoting inside the block);
-//                          U'_i = D_i^-1 U_i,  b'_i = D_i^-1 b_i
-//   backward:              x_i = b'_i - U'_i x_{i+1}
-// 4 2/3 S^3 flops per block row, 3/7 of them in the Schur-complement DGEMM (cuBLAS: FP64 tensor cores), the rest in
-// cuSOLVER getrf / getrs.  Library baseline of this engine: hand-written kernels for it are the next step.
-int block_thomas_solve(yhb_plan *pl, double *J, double *rhs, cudaStream_t st) {
-    const PlanDev &d = pl->d;
+// Panel Gauss-Jordan of nsys systems (yhb_dense.cuh): per panel of 16 pivot columns one factorisation launch and
+// one DMMA trailing-update launch over the remaining columns.
+int gjp_run(const GjpBatch &g, int nsys, cudaStream_t st) {
+    const int npanel = (g.n + kGjpNB - 1) / kGjpNB;
+    const int nt = std::min(1024, (g.n + 31) & ~31);
+    const size_t smem = (size_t)kGjpNB * (g.n | 1) * sizeof(double);
+    if (smem > 227 * 1024 - 1024) { set_error("panel Gauss-Jordan: more than 14 000 pivots per system"); return -4; }
+    if (smem > 48 * 1024)
+        YHB_CUDA(cudaFuncSetAttribute(k_gjp_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int j = 0; j < npanel; ++j) {
+        k_gjp_panel<<<nsys, nt, smem, st>>>(g, j);
+        const int rem = g.ncols - (j + 1) * kGjpNB;
+        if (rem <= 0) continue;
+        // wide column chunks once there are enough CTAs to fill the GPU several times over
+        if ((long)((rem + 15) / 16) * nsys >= 1200) {
+            k_gjp_update<32><<<dim3((rem + 31) / 32, nsys), 256, 0, st>>>(g, j);
+        } else {
+            k_gjp_update<16><<<dim3((rem + 15) / 16, nsys), 256, 0, st>>>(g, j);
+        }
+    }
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+GjpBatch gjp_batch(const Workspace &ws, const int *list) {
+    GjpBatch g;
+    memset(&g, 0, sizeof(g));
+    g.M = ws.J;
+    g.m_stride = ws.j_stride;
+    g.L = ws.gj_L;
+    g.piv = ws.gj_piv;
+    g.rowof = ws.gj_rowof;
+    g.used = ws.gj_used;
+    g.pp = ws.gj_pp;
+    g.fail = ws.gj_fail;
+    g.list = list;
+    g.count = nullptr;  // the host knows the number of queued circuits: grids are sized exactly
+    g.n = ws.gj_n;
+    g.lpad = ws.gj_lpad;
+    return g;
+}
+
+// Block-Thomas elimination of the queued circuits' block-tridiagonal cores (blocks as k_assemble_btd laid them out;
+// right-hand sides in the block rows, solution into ws.rhs), all circuits concurrently:
+//   forward, block row r:  [D_r | rhs_r] -= L_r [U'_{r-1} | b'_{r-1}]              (k_btd_schur: DMMA GEMM + GEMV)
+//                          Gauss-Jordan of [D_r | U_r | rhs_r] with partial pivoting inside D_r (gjp_run)
+//                          U'_r = D_r^-1 U_r -> storage of L_r,  b'_r = D_r^-1 rhs_r -> ws.rhs     (k_gjp_finish)
+//   backward:              x_r = b'_r - U'_r x_{r+1}                                               (k_btd_back)
+int block_thomas_solve(const PlanDev &d, const Workspace &ws, const int *list, int nsolve, cudaStream_t st) {
     const int S = d.S, Nc = d.Nc;
-    if (!pl->blas) {
-        if (cublasCreate(&pl->blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return -2; }
-        if (cusolverDnCreate(&pl->solver) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed"); return -2; }
-        if (cusolverDnDgetrf_bufferSize(pl->solver, S, S, J, S, &pl->btd_lwork) != CUSOLVER_STATUS_SUCCESS) {
-            set_error("cusolverDnDgetrf_bufferSize failed");
-            return -2;
+    GjpBatch g = gjp_batch(ws, list);
+    g.ld = btd_ldm(S);
+    g.ncols = 2 * S + 1;
+    SchurArgs sa;
+    sa.J = ws.J;
+    sa.j_stride = ws.j_stride;
+    sa.rhs = ws.rhs;
+    sa.rhs_stride = (size_t)d.Wc + 1;
+    sa.list = list;
+    sa.count = nullptr;
+    sa.S = S;
+    const int ntx = (S + kSchurBN - 1) / kSchurBN, nty = (S + kSchurBM - 1) / kSchurBM;
+    for (int r = 0; r < Nc; ++r) {
+        if (r > 0) {
+            sa.r = r;
+            k_btd_schur<<<dim3(ntx + 1, nty, nsolve), 256, 0, st>>>(sa);
         }
-        YHB_CUDA(cudaMalloc(&pl->btd_work, sizeof(double) * std::max(pl->btd_lwork, 1)));
-        YHB_CUDA(cudaMalloc(&pl->btd_ipiv, sizeof(int) * (size_t)S * Nc));
-        YHB_CUDA(cudaMalloc(&pl->btd_info, sizeof(int)));
-    }
-    cublasSetStream(pl->blas, st);
-    cusolverDnSetStream(pl->solver, st);
-    const double one = 1., minus = -1.;
-    const size_t bs = (size_t)S * S;
-    auto blkp = [&](int r, int which) { return J + ((size_t)r * 3 + which) * bs; };
-#define YHB_LIB(call, ok)                                                       \
-    do {                                                                        \
-        if ((call) != (ok)) { set_error(#call " failed"); return -2; }          \
-    } while (0)
-    for (int i = 0; i < Nc; ++i) {
-        double *D = blkp(i, 1), *b = rhs + (size_t)i * S;
-        int *ipiv = pl->btd_ipiv + (size_t)i * S;
-        if (i > 0) {
-            const double *Lo = blkp(i, 0), *Up = blkp(i - 1, 2);
-            YHB_LIB(cublasDgemm(pl->blas, CUBLAS_OP_N, CUBLAS_OP_N, S, S, S, &minus, Lo, S, Up, S, &one, D, S), CUBLAS_STATUS_SUCCESS);
-            YHB_LIB(cublasDgemv(pl->blas, CUBLAS_OP_N, S, S, &minus, Lo, S, b - S, 1, &one, b, 1), CUBLAS_STATUS_SUCCESS);
+        g.m_off = (size_t)r * btd_row_doubles(S);
+        if (int rc = gjp_run(g, nsolve, st)) return rc;
+        GjpFinish f;
+        memset(&f, 0, sizeof(f));
+        if (r + 1 < Nc) {
+            f.out0 = ws.J;
+            f.out0_stride = ws.j_stride;
+            f.out0_off = g.m_off + (size_t)S * btd_ldm(S);
+            f.nout0 = S;
+            f.ld0 = btd_lds(S);
         }
-        YHB_LIB(cusolverDnDgetrf(pl->solver, S, S, D, S, pl->btd_work, ipiv, pl->btd_info), CUSOLVER_STATUS_SUCCESS);
-        if (i + 1 < Nc)
-            YHB_LIB(cusolverDnDgetrs(pl->solver, CUBLAS_OP_N, S, S, D, S, ipiv, blkp(i, 2), S, pl->btd_info), CUSOLVER_STATUS_SUCCESS);
-        YHB_LIB(cusolverDnDgetrs(pl->solver, CUBLAS_OP_N, S, 1, D, S, ipiv, b, S, pl->btd_info), CUSOLVER_STATUS_SUCCESS);
+        f.out1 = ws.rhs;
+        f.out1_stride = (size_t)d.Wc + 1;
+        f.out1_off = (size_t)r * S;
+        f.col1 = S;
+        k_gjp_finish<<<dim3(std::min((S + 7) / 8, 148), nsolve), 256, 0, st>>>(g, f);
     }
-    for (int i = Nc - 2; i >= 0; --i) {
-        double *b = rhs + (size_t)i * S;
-        YHB_LIB(cublasDgemv(pl->blas, CUBLAS_OP_N, S, S, &minus, blkp(i, 2), S, b + S, 1, &one, b, 1), CUBLAS_STATUS_SUCCESS);
+    for (int r = Nc - 2; r >= 0; --r) {
+        sa.r = r;
+        k_btd_back<<<dim3(std::min((S + 7) / 8, 148), nsolve), 256, 0, st>>>(sa);
     }
-#undef YHB_LIB
+    YHB_CUDA(cudaGetLastError());
     return 0;
 }
 
 // the Newton / continuation launch loop shared by yhb_solve and yhb_newton
 int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, Layout &L, int have_v0,
              const double *alpha_fixed, const yhb_result *res, cudaStream_t st) {
-    yhb_plan *pl = const_cast<yhb_plan *>(cpl);  // library handles of the block-Thomas engine are created lazily
+    const yhb_plan *pl = cpl;
     const PlanDev &d = pl->d;
     const int B = p->batch;
     Workspace &ws = L.ws;
@@ -1152,28 +1252,39 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
         YHB_CUDA(cudaMemcpyAsync(hc, ws.count, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         YHB_CUDA(cudaStreamSynchronize(st));
         const int nsolve = hc[cur ^ 1];
-        if (nsolve > 0 && d.btd) {
-            // block-Thomas engine: peeled rows + rhs, blocks, block elimination (library calls), back-substitution
+        if (nsolve > 0 && ws.gj_n > 0) {
+            // panel Gauss-Jordan (dense core) / block-Thomas engine: peeled rows + rhs, assembly, elimination of all
+            // queued circuits concurrently, back-substitution of the peeled rows + update
             const size_t rowbuf = 4;
             {
                 ProfScope ps(PK_LU, st);
                 k_solve_core<<<nsolve, 1024, rowbuf * sizeof(double), st>>>(d, ws, ea, cur ^ 1, 1);
             }
-            {
+            if (d.btd) {
                 dim3 ga(nsolve, 3 * d.Nc, (d.S * d.S + kBtdChunk - 1) / kBtdChunk);
                 ProfScope ps(PK_ASSEMBLE, st);
                 k_assemble_btd<<<ga, 256, 0, st>>>(d, ws, ea, cur ^ 1);
+            } else {
+                dim3 ga(nsolve, (d.Wc + kAsmRows - 1) / kAsmRows);
+                ProfScope ps(PK_ASSEMBLE, st);
+                k_assemble_core<<<ga, 256, 0, st>>>(d, ws, ea, cur ^ 1, gjp_dense_ld(d.Wc));
             }
             YHB_CUDA(cudaGetLastError());
-            pl->btd_list.resize(nsolve);
-            YHB_CUDA(cudaMemcpyAsync(pl->btd_list.data(), ws.list[cur ^ 1], nsolve * sizeof(int), cudaMemcpyDeviceToHost, st));
-            YHB_CUDA(cudaStreamSynchronize(st));
             {
                 ProfScope ps(PK_LU, st);
-                for (int i = 0; i < nsolve; ++i) {
-                    const int b = pl->btd_list[i];
-                    if (int rc = block_thomas_solve(pl, ws.J + (size_t)b * ws.j_stride, ws.rhs + (size_t)b * (d.Wc + 1), st))
-                        return rc;
+                if (d.btd) {
+                    if (int rc = block_thomas_solve(d, ws, ws.list[cur ^ 1], nsolve, st)) return rc;
+                } else {
+                    GjpBatch g = gjp_batch(ws, ws.list[cur ^ 1]);
+                    g.ld = gjp_dense_ld(d.Wc);
+                    g.ncols = d.Wc + 1;
+                    if (int rc = gjp_run(g, nsolve, st)) return rc;
+                    GjpFinish f;
+                    memset(&f, 0, sizeof(f));
+                    f.out1 = ws.rhs;
+                    f.out1_stride = (size_t)d.Wc + 1;
+                    f.col1 = 0;
+                    k_gjp_finish<<<dim3(std::min((d.Wc + 7) / 8, 148), nsolve), 256, 0, st>>>(g, f);
                 }
                 k_solve_core<<<nsolve, 1024, rowbuf * sizeof(double), st>>>(d, ws, ea, cur ^ 1, 2);
             }
@@ -1182,7 +1293,7 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
             if (d.Wc > 0) {
                 dim3 ga(nsolve, (d.Wc + kAsmRows - 1) / kAsmRows);
                 ProfScope ps(PK_ASSEMBLE, st);
-                k_assemble_core<<<ga, 256, 0, st>>>(d, ws, ea, cur ^ 1);
+                k_assemble_core<<<ga, 256, 0, st>>>(d, ws, ea, cur ^ 1, d.Wc);
             }
             {
                 ProfScope ps(PK_LU, st);
@@ -1590,6 +1701,64 @@ extern "C" int yhb_stage_gj(int32_t batch, int32_t n, const double *A, const dou
 #undef YHB_CASE
     YHB_CUDA(cudaGetLastError());
     return 0;
+}
+
+// the panel Gauss-Jordan solver of the staged engines on its own: X[B][n][nrhs] = A^-1 Bm, A[B][n][n] row-major
+namespace yhb {
+__global__ void k_gjp_pack(int n, int nrhs, int ld, const double *A, const double *Bm, double *M) {
+    const size_t b = blockIdx.y;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * ld; e += gridDim.x * blockDim.x) {
+        const int r = e / ld, c = e - r * ld;
+        double v = 0.;
+        if (c < n) v = A[(b * n + r) * n + c];
+        else if (c < n + nrhs) v = Bm[(b * n + r) * nrhs + (c - n)];
+        M[b * (size_t)n * ld + e] = v;
+    }
+}
+}  // namespace yhb
+
+extern "C" int yhb_stage_gjp(int32_t batch, int32_t n, int32_t nrhs, const double *A, const double *Bm, double *X,
+                             void *stream) {
+    if (batch < 1 || n < 1 || nrhs < 1 || !A || !Bm || !X) { set_error("bad argument"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ld = (n + nrhs + 2) & ~1, lpad = (n + 7) & ~7;
+    Carver c{nullptr, 0};
+    auto carve_all = [&](Carver &cv, GjpBatch &g) {
+        g.M = cv.take<double>((size_t)batch * n * ld);
+        g.L = cv.take<double>((size_t)batch * kGjpNB * lpad);
+        g.piv = cv.take<double>((size_t)batch * n);
+        g.rowof = cv.take<int>((size_t)batch * n);
+        g.used = cv.take<int>((size_t)batch * n);
+        g.pp = cv.take<int>((size_t)batch * kGjpNB);
+        g.fail = cv.take<int>(batch);
+    };
+    GjpBatch g;
+    memset(&g, 0, sizeof(g));
+    carve_all(c, g);
+    char *buf = nullptr;
+    YHB_CUDA(cudaMalloc(&buf, align_up(c.off)));
+    Carver c2{buf, 0};
+    carve_all(c2, g);
+    g.m_stride = (size_t)n * ld;
+    g.n = n;
+    g.ld = ld;
+    g.ncols = n + nrhs;
+    g.lpad = lpad;
+    k_gjp_pack<<<dim3(std::max(1, std::min(256, n * ld / 256)), batch), 256, 0, st>>>(n, nrhs, ld, A, Bm, g.M);
+    int rc = gjp_run(g, batch, st);
+    if (rc == 0) {
+        GjpFinish f;
+        memset(&f, 0, sizeof(f));
+        f.out0 = X;
+        f.out0_stride = (size_t)n * nrhs;
+        f.nout0 = nrhs;
+        f.ld0 = nrhs;
+        k_gjp_finish<<<dim3(std::min((n + 7) / 8, 148), batch), 256, 0, st>>>(g, f);
+        if (cudaGetLastError() != cudaSuccess) { set_error("k_gjp_finish launch failed"); rc = -2; }
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(buf);
+    return rc;
 }
 
 extern "C" int yhb_stage_lu(int32_t batch, int32_t W, double *J, const double *F, double *x, void *stream) {

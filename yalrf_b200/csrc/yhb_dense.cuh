@@ -1,0 +1,403 @@
+// Dense-block kernels of the staged engines: Gauss-Jordan elimination with partial pivoting of HBM / L2 resident
+// systems [A | carried columns] by PANELS of 16 pivot columns, for a batch of systems at once.  This is the core
+// solve (:620-621) of
+//   * large dense cores            (BASELINE config 3 at [8,8]: Wc = 289, one system per circuit, carried = rhs), and of
+//   * the block-Thomas engine      (config 5: per block row one system [D_i | U_i | b_i] of S = 1089 pivots with
+//                                   S + 1 carried columns, then the Schur complement of the next block row),
+// which round 1 ran as cuBLAS / cuSOLVER calls from a host loop.  Per panel two launches:
+//   k_gjp_panel   one CTA per system holds the panel's 16 columns of all n rows in shared memory (column-major) and
+//                 factors them: per column ONE barrier -- warp arg-max by redux on the bit pattern of |a| (first row of
+//                 maximal |a| among the rows not yet used: the idamax rule of dgetrf), cross-warp vote through shared
+//                 memory re-reduced by every warp, multipliers l = -(a * (1 / pivot)) as dgetf2 scales them, in-panel
+//                 update of the thread's own rows.  Rows are never moved (implicit pivoting) and rows above the
+//                 pivot are eliminated too (Gauss-Jordan: no triangular solves, full-height rank-16 updates).
+//   k_gjp_update  every CTA owns 16 (or 32) of the remaining columns for ALL rows: stages the 16 pivot rows of its
+//                 columns, completes them (row s is still subject to the panel's earlier pivots), and applies
+//                 A += L (n x 16) . U (16 x cols) with FP64 tensor-core instructions (mma.sync.m8n8k4.f64, DMMA):
+//                 the trailing-update contraction, the only place the tensor pipe is used, as BASELINE.json asks.
+// k_gjp_finish scales the carried columns by the pivots and un-permutes them; k_btd_schur is the DMMA GEMM
+// D_{i+1} -= L_{i+1} U'_i (shared-memory tiles, cp.async double buffering); k_btd_back the back substitution.
+#pragma once
+#include "yhb_internal.cuh"
+
+namespace yhb {
+
+constexpr int kGjpNB = 16;  // pivot columns per panel
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// A batch of systems under elimination.  System index: pos = blockIdx -> s = list ? list[pos] : pos (active circuits).
+struct GjpBatch {
+    double *M;        // working matrices, system s at M + s * m_stride (+ m_off), [n][ld] row-major: [A | carried]
+    size_t m_stride, m_off;
+    double *L;        // multipliers of the current panel, system s at L + s * kGjpNB * lpad: [16][lpad]
+    double *piv;      // [n] per system (stride n): pivot value of every column
+    int *rowof;       // [n] per system: row that eliminated column c (-1: no admissible pivot)
+    int *used;        // [n] per system: row has been a pivot row
+    int *pp;          // [16] per system: pivot rows of the current panel (-1: none)
+    int *fail;        // per system: a column had no admissible pivot (all NaN): the solution is reported as NaN
+    const int *list;  // optional indirection (staged engine's active list) and its length
+    const int *count;
+    int n, ld, ncols, lpad;
+};
+
+__device__ __forceinline__ int gjp_system(const GjpBatch &g, int pos) {
+    if (g.count && pos >= *g.count) return -1;
+    return g.list ? g.list[pos] : pos;
+}
+
+// warp-wide arg-max of (key_hi, key_lo) with ties to the lowest row; key_hi == 0 means "no candidate"
+__device__ __forceinline__ void gjp_warp_best(unsigned &hi, unsigned &lo, int &row) {
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const bool c1 = hi == mhi && mhi != 0u;
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+    const bool c2 = c1 && lo == mlo;
+    const unsigned r = __reduce_min_sync(0xffffffffu, c2 ? (unsigned)row : 0x7fffffffu);
+    hi = mhi;
+    lo = mlo;
+    row = mhi != 0u ? (int)r : -1;
+}
+
+// Panel j (columns 16 j .. 16 j + 15 of A) of every system.  Dynamic shared memory: 16 * npad doubles, npad = n | 1.
+__global__ void __launch_bounds__(1024) k_gjp_panel(GjpBatch g, int j) {
+    extern __shared__ double P[];  // [16][npad] column-major panel; column s holds its multipliers once it is eliminated
+    __shared__ unsigned s_hi[2][32], s_lo[2][32];
+    __shared__ int s_row[2][32];
+    const int sys = gjp_system(g, blockIdx.x);
+    if (sys < 0) return;
+    const int n = g.n, ld = g.ld, npad = n | 1, lpad = g.lpad;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
+    double *Lg = g.L + (size_t)sys * kGjpNB * lpad;
+    int *used = g.used + (size_t)sys * n;
+    const int col0 = j * kGjpNB;
+    const int nb = min(kGjpNB, n - col0);
+    for (int idx = tid; idx < n * kGjpNB; idx += nt) {
+        const int r = idx >> 4, c = idx & 15;
+        P[c * npad + r] = c < nb ? M[(size_t)r * ld + col0 + c] : 0.;
+    }
+    unsigned um = 0;  // bit k: this thread's k-th row (tid + k nt) has been a pivot row
+    if (j > 0) {
+        int k = 0;
+        for (int r = tid; r < n; r += nt, ++k) um |= (used[r] ? 1u : 0u) << k;
+    } else {
+        for (int r = tid; r < n; r += nt) used[r] = 0;  // a new system: the flags of the previous one are stale
+    }
+    if (j == 0 && tid == 0) g.fail[sys] = 0;
+    __syncthreads();
+    for (int s = 0; s < kGjpNB; ++s) {
+        double *Ps = P + s * npad;
+        if (s >= nb) {  // past the last column: empty steps keep the update kernel uniform
+            for (int r = tid; r < n; r += nt) Lg[(size_t)s * lpad + r] = 0.;
+            if (tid == 0) g.pp[sys * kGjpNB + s] = -1;
+            continue;
+        }
+        // arg-max of |a| over the rows not yet used; NaN entries never win (comparison false)
+        double best = -1.;
+        int bi = -1;
+        {
+            int k = 0;
+            for (int r = tid; r < n; r += nt, ++k) {
+                const double v = fabs(Ps[r]);
+                if (!((um >> k) & 1u) && v > best) { best = v; bi = r; }
+            }
+        }
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(best);
+        unsigned hi = bi >= 0 ? (unsigned)(bits >> 32) + 1u : 0u, lo = (unsigned)bits;
+        int row = bi;
+        gjp_warp_best(hi, lo, row);
+        const int par = s & 1;
+        if (lane == 0) { s_hi[par][warp] = hi; s_lo[par][warp] = lo; s_row[par][warp] = row; }
+        __syncthreads();
+        hi = lane < nwarp ? s_hi[par][lane] : 0u;
+        lo = lane < nwarp ? s_lo[par][lane] : 0u;
+        row = lane < nwarp ? s_row[par][lane] : -1;
+        gjp_warp_best(hi, lo, row);
+        const int p = row;  // identical in every thread
+        if (tid == 0) {
+            g.pp[sys * kGjpNB + s] = p;
+            g.rowof[(size_t)sys * n + col0 + s] = p;
+            g.piv[(size_t)sys * n + col0 + s] = p >= 0 ? Ps[p] : 0.;
+            if (p < 0) g.fail[sys] = 1;
+        }
+        if (p < 0) {  // no admissible pivot: the column is skipped, the system is reported as NaN
+            for (int r = tid; r < n; r += nt) Lg[(size_t)s * lpad + r] = 0.;
+            continue;
+        }
+        const double rinv = 1. / Ps[p];
+        int k = 0;
+        for (int r = tid; r < n; r += nt, ++k) {
+            if (r == p) {
+                um |= 1u << k;
+                used[r] = 1;
+                Lg[(size_t)s * lpad + r] = 0.;
+                continue;
+            }
+            const double l = -(Ps[r] * rinv);
+            Lg[(size_t)s * lpad + r] = l;
+            for (int s2 = s + 1; s2 < nb; ++s2) {
+                double *q = P + s2 * npad;
+                q[r] = fma(l, q[p], q[r]);
+            }
+        }
+        // the next step's barrier orders these writes (own rows only) before any other thread reads row p' of them
+    }
+}
+
+// Trailing update of panel j: columns c0 = 16 (j + 1) + CW * blockIdx.x ... of system blockIdx.y, all rows.
+template <int CW>
+__global__ void __launch_bounds__(256) k_gjp_update(GjpBatch g, int j) {
+    __shared__ double Us[kGjpNB][CW + 4];
+    __shared__ double Ts[kGjpNB][kGjpNB];
+    __shared__ int pps[kGjpNB];
+    const int sys = gjp_system(g, blockIdx.y);
+    if (sys < 0) return;
+    const int n = g.n, ld = g.ld, lpad = g.lpad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
+    const double *Lg = g.L + (size_t)sys * kGjpNB * lpad;
+    const int c0 = (j + 1) * kGjpNB + CW * blockIdx.x;
+    if (c0 >= g.ncols) return;
+    if (tid < kGjpNB) pps[tid] = g.pp[sys * kGjpNB + tid];
+    __syncthreads();
+    // T[s][s'] = l_{s'}[p_s], s' < s: what pivot row s still owes to the panel's earlier pivots
+    {
+        const int s = tid >> 4, s1 = tid & 15;
+        Ts[s][s1] = (s1 < s && pps[s] >= 0 && pps[s1] >= 0) ? Lg[(size_t)s1 * lpad + pps[s]] : 0.;
+    }
+    for (int idx = tid; idx < kGjpNB * CW; idx += 256) {
+        const int s = idx / CW, c = idx - s * CW;
+        Us[s][c] = (pps[s] >= 0 && c0 + c < g.ncols) ? M[(size_t)pps[s] * ld + c0 + c] : 0.;
+    }
+    __syncthreads();
+    if (tid < CW) {  // u_s += sum_{s' < s} T[s][s'] u_{s'}, sequential in s
+        double u[kGjpNB];
+#pragma unroll
+        for (int s = 0; s < kGjpNB; ++s) {
+            double a0 = Us[s][tid], a1 = 0.;
+#pragma unroll
+            for (int s1 = 0; s1 + 1 < s; s1 += 2) {
+                a0 = fma(Ts[s][s1], u[s1], a0);
+                a1 = fma(Ts[s][s1 + 1], u[s1 + 1], a1);
+            }
+            if (s & 1) a0 = fma(Ts[s][s - 1], u[s - 1], a0);
+            u[s] = a0 + a1;
+            Us[s][tid] = u[s];
+        }
+    }
+    __syncthreads();
+    // rank-16 update on the tensor pipe: rows 8 rt .. 8 rt + 7, column tiles of 8
+    const int gq = lane >> 2, t = lane & 3;
+    constexpr int NCT = CW / 8;
+    double bf[NCT][4];
+#pragma unroll
+    for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) bf[ct][kk] = Us[4 * kk + t][8 * ct + gq];
+    const int nrt = (n + 7) >> 3;
+    for (int rt = warp; rt < nrt; rt += 8) {
+        const int r = 8 * rt + gq;
+        const bool rok = r < n;
+        double a[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) a[kk] = rok ? Lg[(size_t)(4 * kk + t) * lpad + r] : 0.;
+        double *crow = M + (size_t)(rok ? r : 0) * ld + c0 + 2 * t;
+        double2 cv[NCT];
+#pragma unroll
+        for (int ct = 0; ct < NCT; ++ct) {
+            const bool cok = rok && c0 + 8 * ct + 2 * t < g.ncols;  // ld is even and > ncols: a pair never leaves the row
+            cv[ct] = cok ? *reinterpret_cast<const double2 *>(crow + 8 * ct) : make_double2(0., 0.);
+        }
+#pragma unroll
+        for (int ct = 0; ct < NCT; ++ct)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) dmma884(cv[ct].x, cv[ct].y, a[kk], bf[ct][kk]);
+#pragma unroll
+        for (int ct = 0; ct < NCT; ++ct) {
+            const bool cok = rok && c0 + 8 * ct + 2 * t < g.ncols;
+            if (cok) *reinterpret_cast<double2 *>(crow + 8 * ct) = cv[ct];
+        }
+    }
+}
+
+// Carried columns -> solution: X[c][k] = M[rowof[c]][n + k] / piv[c].  out0 (optional): columns 0 .. nout0 - 1 of the
+// carried block, [n][ld0] row-major (pad columns zeroed); out1 (optional): carried column col1 as a vector [n].
+struct GjpFinish {
+    double *out0;
+    size_t out0_stride, out0_off;
+    int nout0, ld0;
+    double *out1;
+    size_t out1_stride, out1_off;
+    int col1;
+};
+
+__global__ void __launch_bounds__(256) k_gjp_finish(GjpBatch g, GjpFinish f) {
+    const int sys = gjp_system(g, blockIdx.y);
+    if (sys < 0) return;
+    const int n = g.n, ld = g.ld;
+    const double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const int fail = g.fail[sys];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * 8 + warp; c < n; c += gridDim.x * 8) {
+        const int r = g.rowof[(size_t)sys * n + c];
+        const double pv = g.piv[(size_t)sys * n + c];
+        const bool bad = fail || r < 0;
+        const double *src = M + (size_t)(bad ? 0 : r) * ld + n;
+        if (f.out0) {
+            double *dst = f.out0 + (size_t)sys * f.out0_stride + f.out0_off + (size_t)c * f.ld0;
+            for (int k = lane; k < f.ld0; k += 32) dst[k] = k < f.nout0 ? (bad ? nan : src[k] / pv) : 0.;
+        }
+        if (f.out1 && lane == 0)
+            f.out1[(size_t)sys * f.out1_stride + f.out1_off + c] = bad ? nan : src[f.col1] / pv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- //
+// Block-Thomas engine: storage of one circuit's block-tridiagonal core (Nc block rows of S x S node blocks)
+//   block row r:  Mr [S][ldm]  = [ D_r | U_r (block (r, r+1)) | rhs_r | pad ],  ldm = 2 S + 2
+//                 Lr [S][lds]  = sub-diagonal block (r, r-1) (pad column zero), lds = S + (S & 1) + ... even;
+//                                after block row r is eliminated its storage holds U'_r = D_r^-1 U_r
+// ---------------------------------------------------------------------------------------------------------------- //
+__host__ __device__ inline int btd_ldm(int S) { return 2 * S + 2; }
+__host__ __device__ inline int btd_lds(int S) { return (S + 2) & ~1; }
+__host__ __device__ inline size_t btd_row_doubles(int S) { return (size_t)S * btd_ldm(S) + (size_t)S * btd_lds(S); }
+
+// C[S x S] (leading S columns of Mr) -= A (Lr, [S][lds]) . B (U'_{r-1}, [S][lds]);  rhs column -= A . x (b'_{r-1}).
+// 64 x 64 tiles, k slabs of 16 staged in shared memory by cp.async (double buffered), 8 warps of 16 x 32 outputs each.
+constexpr int kSchurBM = 64, kSchurBN = 64, kSchurBK = 16;
+struct SchurArgs {
+    double *J;        // circuit b at J + b * j_stride
+    size_t j_stride;
+    double *rhs;      // [B][Wc + 1]: b' of the eliminated block rows / rhs of the others
+    size_t rhs_stride;
+    const int *list, *count;
+    int S, r;         // block row being updated (r >= 1)
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+
+__global__ void __launch_bounds__(256) k_btd_schur(SchurArgs a) {
+    __shared__ __align__(16) double As[2][kSchurBM][kSchurBK + 4];
+    __shared__ __align__(16) double Bs[2][kSchurBK][kSchurBN + 4];
+    const int pos = blockIdx.z;
+    if (a.count && pos >= *a.count) return;
+    const int b = a.list ? a.list[pos] : pos;
+    const int S = a.S, ldm = btd_ldm(S), lds = btd_lds(S);
+    double *Jb = a.J + (size_t)b * a.j_stride;
+    double *Mr = Jb + (size_t)a.r * btd_row_doubles(S);
+    const double *A = Mr + (size_t)S * ldm;                                             // L_r
+    const double *Bm = Jb + (size_t)(a.r - 1) * btd_row_doubles(S) + (size_t)S * ldm;   // U'_{r-1}
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blockIdx.y * kSchurBM;
+    const int ntx = (S + kSchurBN - 1) / kSchurBN;
+    if ((int)blockIdx.x == ntx) {
+        // right-hand side: rhs_r[row] -= sum_k A[row][k] b'_{r-1}[k], one warp per row
+        const double *x = a.rhs + (size_t)b * a.rhs_stride + (size_t)(a.r - 1) * S;
+        for (int rr = warp; rr < kSchurBM; rr += 8) {
+            const int row = r0 + rr;
+            if (row >= S) break;
+            const double *ar = A + (size_t)row * lds;
+            double acc = 0.;
+            for (int k = lane; k < S; k += 32) acc = fma(ar[k], x[k], acc);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+            if (lane == 0) Mr[(size_t)row * ldm + 2 * S] -= acc;
+        }
+        return;
+    }
+    const int c0 = blockIdx.x * kSchurBN;
+    const int nk = (S + kSchurBK - 1) / kSchurBK;
+    auto stage = [&](int buf, int kt) {
+        const int k0 = kt * kSchurBK;
+        // A tile: 64 rows x 16 k = 512 chunks of 2 doubles... 16-byte chunks: 8 per row
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int ch = tid + 256 * i;
+            const int rr = ch >> 3, kc = (ch & 7) * 2;
+            const bool ok = r0 + rr < S && k0 + kc < lds;
+            cp_async16(&As[buf][rr][kc], A + (size_t)(ok ? r0 + rr : 0) * lds + (ok ? k0 + kc : 0), ok);
+        }
+        // B tile: 16 k x 64 columns: 32 chunks per row
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int ch = tid + 256 * i;
+            const int kk = ch >> 5, cc = (ch & 31) * 2;
+            const bool ok = k0 + kk < S && c0 + cc < lds;
+            cp_async16(&Bs[buf][kk][cc], Bm + (size_t)(ok ? k0 + kk : 0) * lds + (ok ? c0 + cc : 0), ok);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    const int gq = lane >> 2, t = lane & 3;
+    const int wr = (warp >> 1) * 16, wc = (warp & 1) * 32;
+    double c[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) c[i][jj][0] = c[i][jj][1] = 0.;
+    stage(0, 0);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) {
+            stage(buf ^ 1, kt + 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
+        // columns k >= S of A's last slab hold the pad column (zero) or zero fill; rows k >= S of B are zero filled
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            double af[2], bfr[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = -As[buf][wr + 8 * i + gq][4 * kk + t];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) bfr[jj] = Bs[buf][4 * kk + t][wc + 8 * jj + gq];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) dmma884(c[i][jj][0], c[i][jj][1], af[i], bfr[jj]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int row = r0 + wr + 8 * i + gq;
+        if (row >= S) continue;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int col = c0 + wc + 8 * jj + 2 * t;
+            double *dst = Mr + (size_t)row * ldm + col;
+            if (col < S) dst[0] += c[i][jj][0];
+            if (col + 1 < S) dst[1] += c[i][jj][1];
+        }
+    }
+}
+
+// back substitution of the block-Thomas chain: x_r = b'_r - U'_r x_{r+1}, in place in rhs.  grid (row chunks, circuits)
+__global__ void __launch_bounds__(256) k_btd_back(SchurArgs a) {
+    const int pos = blockIdx.y;
+    if (a.count && pos >= *a.count) return;
+    const int b = a.list ? a.list[pos] : pos;
+    const int S = a.S, ldm = btd_ldm(S), lds = btd_lds(S);
+    const double *U = a.J + (size_t)b * a.j_stride + (size_t)a.r * btd_row_doubles(S) + (size_t)S * ldm;  // U'_r
+    double *x = a.rhs + (size_t)b * a.rhs_stride + (size_t)a.r * S;
+    const double *xn = x + S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * 8 + warp; row < S; row += gridDim.x * 8) {
+        const double *ur = U + (size_t)row * lds;
+        double acc = 0.;
+        for (int k = lane; k < S; k += 32) acc = fma(ur[k], xn[k], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) x[row] -= acc;
+    }
+}
+
+}  // namespace yhb

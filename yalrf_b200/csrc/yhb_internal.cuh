@@ -163,6 +163,15 @@ struct Workspace {
     double *xstep;       // [B][x_stride]  staged engine: Newton step vector + scratch of newton_pre / newton_post
     size_t x_stride;
     double *rhs;         // [B][Wc+1]
+    // panel Gauss-Jordan solver of the staged engines (yhb_dense.cuh), per circuit; gj_n = pivots per system
+    // (Wc for a dense core, S for the block rows of the block-Thomas engine), 0 = not used by this plan
+    int gj_n, gj_lpad;
+    double *gj_L;        // [B][16][gj_lpad] multipliers of the current panel
+    double *gj_piv;      // [B][gj_n]
+    int *gj_rowof;       // [B][gj_n]
+    int *gj_used;        // [B][gj_n]
+    int *gj_pp;          // [B][16]
+    int *gj_fail;        // [B]
     int *list[2];        // [B] active-circuit lists (ping-pong)
     int *count;          // [4] device counters: active[0], active[1], done, spare
     int32_t *level_iters;  // [B][YHB_MAX_LEVELS]
