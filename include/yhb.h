@@ -215,6 +215,15 @@ int yhb_dc_solve(const yhb_plan *plan, const yhb_params *p, void *ws, size_t ws_
 int yhb_solve(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt, void *ws,
               size_t ws_bytes, int32_t have_v0, const double *Vdc, const yhb_result *res, void *stream);
 
+/* Cold run() as ONE call: calc_V0 (:321-324 -> DC.run) and the source-stepping ladder (:338-384).  On the fused (on-chip)
+ * engine the batched DC analysis runs BESIDE the harmonic-balance kernel -- on a high-priority side stream of the plan,
+ * forked from and joined into `stream` by events; the HB kernel takes the circuits in the DC kernel's order (strongest
+ * drive first, so that its last wave of circuits is the cheapest) and waits for each operating point -- instead of in
+ * front of it; the staged engines run the two one after the other.  Vdc[B][N] / dc_info[B][2] (optional outputs) as in
+ * yhb_dc_solve.  A circuit whose operating point never arrived reports converged = -2. */
+int yhb_solve_cold(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt, void *ws, size_t ws_bytes,
+                   double *Vdc, int32_t *dc_info, const yhb_result *res, void *stream);
+
 /* one hb_loop (:407-631) at source-stepping factor alpha[B] from res->V */
 int yhb_newton(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt, void *ws,
                size_t ws_bytes, const double *alpha, const yhb_result *res, void *stream);
@@ -223,6 +232,47 @@ int yhb_newton(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt
  * synchronous.  V0 (host, [B][W]) may be NULL for cold starts.  This is the end-to-end entry. */
 int yhb_run_host(const yhb_plan *plan, const yhb_params *host_params, const yhb_options *opt,
                  const double *V0, const yhb_result *host_res);
+
+/* ---- autonomous oscillators: run_oscillator (:137-232) ----------------------------------------------------------
+ * The netlist handed to yhb_plan_create already contains the reference's oscillator probe (:146-150): AC current
+ * source (amplitude = Vosc) -> unit gyrator -> IdealHarmonicFilter -> probed node.  The GPU owns the outer iteration
+ * that replaces scipy.optimize.fmin (:204-212): a damped 2 x 2 Newton iteration on (fosc, Vosc) solving
+ * Yosc = Iosc / V(node) = 0 (:183-196), the probe current taken from Kirchhoff's law at the node and the Jacobian from
+ * two extra right-hand sides of the already factored HB Jacobian; one inner HB solve per outer iteration, the whole
+ * batch (start points, parameter sweeps) advances together.  Fused (on-chip) engine, one tone. */
+typedef struct {
+    size_t struct_size;    /* sizeof(yhb_osc_options) */
+    int32_t probe_src;     /* index (source table) of the probe current source: its ac amplitude is Vosc          */
+    int32_t probe_filter;  /* index (linear table) of the probe IdealHarmonicFilter: its freq follows fosc        */
+    int32_t node;          /* probed node, reference numbering                                                    */
+    int32_t max_outer;     /* outer iterations, 0 = 30                                                            */
+    double tol;            /* |Yosc| target in S, 0 = 1e-12 (the reference's early exit, :191)                    */
+    double max_df_rel;     /* trust region of one outer step, relative: 0 = 0.02 in frequency ...                 */
+    double max_dv_rel;     /* ... 0 = 0.3 in amplitude                                                            */
+} yhb_osc_options;
+
+typedef struct {
+    size_t struct_size;       /* sizeof(yhb_osc_result) */
+    double *fosc;             /* [B]  in: start frequency f0, out: oscillation frequency (also hb.freq, :226)      */
+    double *Vosc;             /* [B]  in: start amplitude V0, out: oscillation amplitude                          */
+    double *yosc;             /* [B][2]  Re, Im of Yosc at the returned point (may be NULL)                       */
+    int32_t *converged;       /* [B]  (may be NULL)                                                               */
+    int32_t *outer_iters;     /* [B]  accepted outer iterations (may be NULL)                                     */
+    int32_t *hb_newton_iters; /* [B]  Newton iterations of all inner HB solves (may be NULL)                      */
+    double *diag;             /* [B][8]  diagnostics at the returned point (may be NULL): the 2 x 2 Jacobian
+                                 d(Re Yosc, Im Yosc) / d(f, V) row-major, the next Newton step (df, dV), its damping,
+                                 1.0 if the outer iteration gave up                                               */
+} yhb_osc_result;
+
+/* Device pointers.  p's tones / lin_val (probe filter) / src_val (probe source) are REWRITTEN every outer iteration and
+ * hold the returned point afterwards.  res = the HB result at the returned point (as the final self.run of :226-227).
+ * Synchronises the stream once per outer iteration (it reads back how many oscillators are still iterating). */
+int yhb_solve_oscillator(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt,
+                         const yhb_osc_options *osc, void *ws, size_t ws_bytes, const yhb_result *res,
+                         const yhb_osc_result *osc_res, void *stream);
+/* the same with HOST buffers (H2D / D2H inside, synchronous); the host parameter arrays are not modified */
+int yhb_oscillator_host(const yhb_plan *plan, const yhb_params *host_params, const yhb_options *opt,
+                        const yhb_osc_options *osc, const yhb_result *host_res, const yhb_osc_result *host_osc_res);
 
 /* ---- stage entry points (parity tests / profiling); device pointers -------------------------------- */
 /* ifft (:706-713): vt[B][W] = IDFT applied per node */

@@ -34,5 +34,7 @@ for nh in ([3, 3], [8, 8]):
 y = yalrf_b200.Netlist('o'); h = circuits.peltz(y)
 hb = MultiToneHarmonicBalance('HB1')
 t = time.perf_counter(); hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node']); res['cfg2_peltz_oscillator_s'] = time.perf_counter() - t
-res['cfg2_evals'] = len(hb.osc_evals); res['cfg2_fosc'] = hb.fosc
+res['cfg2_outer_iterations'] = int(hb.last_osc.outer_iterations[0]); res['cfg2_fosc'] = hb.fosc; res['cfg2_Vosc'] = hb.Vosc; res['cfg2_yosc'] = hb.osc_yosc
+f0 = np.linspace(70e3, 90e3, 64); V0 = np.linspace(0.05, 0.8, 64)
+dt, r = timeit(lambda: hb.run_oscillator_batch(y, f0, h['K'], V0, h['node']), reps=2); res['cfg2_batch64_oscillators_per_s'] = 64 / dt; res['cfg2_batch64_converged'] = int(r.converged.sum())
 print(json.dumps(res, indent=1))

@@ -265,3 +265,26 @@ def ring(y, n=4, ac=0.5, seed=1):
         d = y.add_diode('D%d' % i, 'n%d' % i, 'gnd')
         d.options['Is'] = 1e-15 * float(10.0 ** rng.uniform(-0.05, 0.05))
     return dict(freq=1e6, K=4)
+
+
+def stiff_pair(y, ac=3.0, rc=1e-3, rleak=1e9):
+    """Not a reference script: an adversarial core for pivoting INSIDE node blocks.  Two diode nodes tied together by a
+    1 mOhm resistor (1e3 S on both diagonal blocks and between them) and to everything else only through leakage: each
+    diagonal block alone is well conditioned, but the pair's difference mode is 12 decades below its common mode, so
+    a factorisation that eliminates node a inside its own block has to carry the cancellation through the Schur
+    complement of node b -- LAPACK on the dense matrix would interleave the rows of both nodes.  Strong drive: the
+    diode conductance waveforms span many decades."""
+    y.add_iac('I1', 'nx', 'gnd', ac=ac, freq=1e6)
+    y.add_gyrator('G1', 'nx', 'ns', 'gnd', 'gnd', 1)
+    y.add_resistor('Rs', 'ns', 'na', 100)
+    y.add_resistor('Rc', 'na', 'nb', rc)
+    y.add_resistor('Ra', 'na', 'gnd', rleak)
+    y.add_resistor('Rb', 'nb', 'nc', 50)
+    y.add_resistor('Rl', 'nc', 'gnd', rleak)
+    da = y.add_diode('Da', 'na', 'gnd')
+    db = y.add_diode('Db', 'gnd', 'nb')
+    dc = y.add_diode('Dc', 'nc', 'gnd')
+    da.options['Is'] = 1e-15
+    db.options['Is'] = 3e-15
+    dc.options['Is'] = 1e-14
+    return dict(freq=1e6, K=6)

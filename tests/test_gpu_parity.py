@@ -333,8 +333,18 @@ def test_vanderpol_oscillator(yb, golden):
     hb = mthb('HB1')
     conv, freqs, Vf, _, _ = hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node'])
     assert conv
-    assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 1e-8
-    assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 1e-8
+    # the fixture is the reference's Nelder-Mead answer (xtol 1e-12 on a simplex that stalls at the 1e-8 level: measured
+    # distance from the Newton root 2.8e-8 in Vosc); the device Newton iteration itself ends at |Yosc| < 1e-12
+    assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 1e-7
+    assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 1e-7
+    assert hb.osc_yosc < 1e-12
+    # the reference's own outer loop replayed on the GPU solves lands on the fixture to 1e-8
+    hb2 = mthb('HB1')
+    hb2.osc_method = 'fmin'
+    conv2, _, _, _, _ = hb2.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node'])
+    assert conv2
+    assert abs(hb2.fosc - float(g['fosc'])) / float(g['fosc']) < 1e-8
+    assert abs(hb2.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 1e-8
 
 
 def test_oscillator_newton_batch(yb, golden):
@@ -392,6 +402,59 @@ def test_vanderpol_newton(yb, golden):
     assert abs(r.fosc[0] - float(g['fosc'])) / float(g['fosc']) < 1e-7
     assert abs(r.Vosc[0] - float(g['Vosc'])) / float(g['Vosc']) < 1e-7
     assert abs(r.fosc[1] - r.fosc[0]) / r.fosc[0] < 1e-9
+
+
+def test_peltz_oscillator_fmin_replay(yb, golden):
+    """hb.osc_method = 'fmin': the reference's own Nelder-Mead outer loop (:204-212), every evaluation a GPU solve."""
+    g = golden('peltz_osc')
+    y = yb.Netlist('Oscillator')
+    h = circuits.peltz(y)
+    hb = mthb('HB1')
+    hb.osc_method = 'fmin'
+    conv, freqs, Vf, _, _ = hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node'])
+    assert conv and len(hb.osc_evals) <= 300
+    assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 2e-5
+    assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 5e-5
+
+
+def test_oscillator_sweep_vs_oracle(yb):
+    """a run_oscillator parameter sweep (the reference loops run_oscillator over a component value,
+    tests/HBOscillators.ipynb:3052-3115) as ONE device call, every point checked against the oracle: with the probe
+    fixed at the GPU's (fosc, Vosc) the oracle's own HB solution carries no probe current (KCL objective), and its
+    phasors agree with the GPU's."""
+    from oracle import hb_oracle as ho
+    from yalrf_b200 import _osc
+    from yalrf_b200._flatten import ParamBlock, Topology
+    y = yb.Netlist('Oscillator')
+    h = circuits.peltz(y)
+    hb = mthb('HB1')
+    c = np.array([6e-9, 10e-9, 16e-9])
+    r = hb.run_oscillator_batch(y, 80e3, h['K'], 0.1, h['node'], sweeps=[(h['c1'], 'C', c)], maxiter=40)
+    assert r.converged.all(), (r.converged, r.yosc)
+    assert np.max(r.yosc) < 1e-12
+    assert np.all(r.outer_iterations <= 25)
+    f_lc = 1 / (2 * np.pi * np.sqrt(0.5e-3 * c))
+    assert np.all(np.abs(r.fosc / f_lc - 1) < 0.01)
+    nb = r.netlist.get_node_idx('nb')
+    for k in range(len(c)):
+        yo = ho.FlatNetlist()
+        ho_h = circuits.peltz(yo)
+        ho_h['c1'].C = float(c[k])
+        yo.add_iac('HB1.I.Oscprobe', 'HB1.nosc1', 'gnd', ac=float(r.Vosc[k]), freq=float(r.fosc[k]))
+        yo.add_gyrator('HB1.G.Oscprobe', 'HB1.nosc1', 'HB1.nosc2', 'gnd', 'gnd', 1)
+        yo.add_idealharmonicfilter('HB1IHF.Oscprobe', 'HB1.nosc2', 'nb', float(r.fosc[k]))
+        o = ho.HBOracle('HB1', float(r.fosc[k]), h['K'])
+        assert o.run(yo)[0]
+        for _ in range(3):
+            assert o.run(yo, o.V)[0]
+        topo = Topology(r.netlist, 1, (h['K'],))
+        pb = ParamBlock(topo, float(r.fosc[k]), 1)
+        pb.set(h['c1'], 'C', [float(c[k])])
+        pb.finalize()
+        pz = [d for _, _, d in topo.lin if d.name == 'HB1IHF.Oscprobe'][0]
+        Y = _osc.kcl_yosc(topo, pb, pz, nb, o.V.reshape(1, -1), o.last_Inl.reshape(1, -1), 21)
+        assert abs(Y[0]) < 1e-9, (k, abs(Y[0]))
+        assert relmax(r.V[k], o.V[:, 0]) < 1e-6, k      # same circuit, same probe: the HB solutions agree
 
 
 # ----------------------------------------------------------------------------- fused engine: block-sparse core LU
@@ -724,3 +787,68 @@ def test_swept_tone_moves_harmonic_filters(yb):
     assert relmax(res.V, np.array(ref)) < 1e-12
     n2 = y.get_node_idx('n2') - 1
     assert np.all(np.abs(res.Vf[:, n2, 1]) > 0.3)      # the fundamental passes the filter at every swept point
+
+
+# ----------------------------------------------------------------------------- extensions and adversarial cases
+@pytest.mark.parametrize('circuit', ['diffamp', 'ladder', 'ladder_bt'])
+def test_exact_jacobian_vs_oracle(yb, circuit):
+    """hb.exact_jacobian = True (YHB_FLAG_EXACT_JACOBIAN): dQdV is re-zeroed every iteration instead of
+    accumulating (:413 vs :438-440), which makes Newton quadratic for circuits with junction capacitances and lets
+    the config-5 ladder with Cje = 1e-12 converge.  Against the oracle with the same switch: identical per-level
+    iteration counts, phasors within 1e-9 -- on the fused engine (block-sparse core), the banded staged engine and the
+    block-Thomas engine."""
+    from oracle import hb_oracle as ho
+    if circuit == 'diffamp':
+        build, kw, nh = circuits.diffamp, dict(vin=20e-3), None
+    else:
+        build, kw, nh = circuits.ladder, dict(stages=10, cje=1e-12, ac=0.5), [2, 2]
+    yo = ho.FlatNetlist()
+    ho_h = build(yo, **kw)
+    K = nh if nh is not None else ho_h['K']
+    o = ho.HBOracle('HB1', ho_h['freq'], K, exact_jacobian=True)
+    conv_o = o.run(yo)[0]
+    o_acc = ho.HBOracle('HB1', ho_h['freq'], K)         # the reference's accumulating Jacobian, for contrast
+    yo2 = ho.FlatNetlist()
+    build(yo2, **kw)
+    o_acc.run(yo2)
+    y = yb.Netlist('x')
+    h = build(y, **kw)
+    hb = mthb('HB1', h['freq'], K)
+    hb.exact_jacobian = True
+    if circuit == 'ladder_bt':
+        hb.engine = 'staged'
+        hb.block_thomas = True
+    elif circuit == 'ladder':
+        hb.engine = 'staged'
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv and conv_o
+    assert hb.last.levels() == [l[1] for l in o.level_log]
+    assert relmax(hb.V, o.V) < 1e-9
+    assert sum(hb.last.levels()) <= o_acc.total_newton          # never slower than the accumulating Jacobian
+    if circuit == 'ladder_bt':
+        assert hb._plan.engine() == 'staged-block-thomas'
+
+
+@pytest.mark.parametrize('ac', [0.5, 3.0])
+def test_block_pivoting_adversarial(yb, ac):
+    """Pivoting restricted to the diagonal node blocks (bs_factor_row) on a core that punishes it: two diode nodes tied
+    by 1 mOhm (circuits.stiff_pair).  The block-sparse LU (forced), the dense tensor-core Gauss-Jordan with pivoting
+    over all rows, and the oracle (LAPACK dgetrf on the full matrix) must walk the same Newton path: identical
+    per-level iteration counts, phasors within 1e-9."""
+    from oracle import hb_oracle as ho
+    yo = ho.FlatNetlist()
+    h = circuits.stiff_pair(yo, ac=ac)
+    o = ho.HBOracle('HB1', h['freq'], h['K'])
+    conv_o = o.run(yo)[0]
+    assert conv_o
+    for mode in (True, False):
+        y = yb.Netlist('stiff')
+        circuits.stiff_pair(y, ac=ac)
+        hb = mthb('HB1', h['freq'], h['K'])
+        hb.block_sparse = mode
+        conv, freqs, Vf, _, _ = hb.run(y)
+        assert hb._plan.engine() == 'fused'
+        assert (hb._plan.block_sparse() >= 2) if mode else hb._plan.block_sparse() == 0
+        assert conv
+        assert hb.last.levels() == [l[1] for l in o.level_log], mode
+        assert relmax(hb.V, o.V) < 1e-9, mode

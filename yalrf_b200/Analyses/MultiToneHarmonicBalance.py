@@ -165,11 +165,39 @@ class MultiToneHarmonicBalance:
 
     # ------------------------------------------------------------------ oscillator (:137-232)
     def run_oscillator(self, netlist, f0, numharmonics, V0, node, useprev=False):
-        """Autonomous-oscillator analysis with the reference's formulation: an oscillator probe (AC current source
-        + gyrator = voltage source, in series with an IdealHarmonicFilter that is a short only at the fundamental)
-        and Nelder-Mead on (fosc, Vosc) minimising |Yosc| = |probe current / probe voltage| (:182-196).  Every
-        objective evaluation is one warm-started GPU solve.  Same arguments, prints and return value as the
-        reference; the optimiser call is the reference's own (scipy.optimize.fmin, :204-212)."""
+        """Autonomous-oscillator analysis (:137-232), same arguments, prints and return value as the reference.  The
+        reference's formulation is kept -- oscillator probe (AC current source + gyrator = voltage source, in series
+        with an IdealHarmonicFilter that is a short only at the fundamental), find (fosc, Vosc) with Yosc = probe
+        current / probe voltage = 0 (:182-196) -- but the outer iteration that the reference leaves to
+        scipy.optimize.fmin (:204-212) runs on the GPU: yhb_oscillator_host, a 2 x 2 Newton iteration with the exact
+        Jacobian (csrc/yhb_osc.cuh).  ``hb.osc_method = 'fmin'`` replays the reference's Nelder-Mead instead (every
+        objective evaluation one GPU solve), which reproduces its evaluation path."""
+        if getattr(self, 'osc_method', 'newton') == 'fmin':
+            return self._run_oscillator_fmin(netlist, f0, numharmonics, V0, node, useprev)
+        from .. import _osc
+        if useprev and getattr(self, 'fosc', None) is not None:
+            f0, V0 = self.fosc, self.Vosc      # the reference warm-starts from self.V (:168-169); here: the last point
+        res = _osc.solve(self, netlist, float(f0), numharmonics, float(V0), node)
+        self.last_osc = res
+        self.netlist = res.netlist
+        fosc, Vosc = float(res.fosc[0]), float(res.Vosc[0])
+        probe_i, probe_z = res.probe
+        probe_i.ac, probe_i.freq, probe_z.freq = Vosc, fosc, fosc       # the probe is left at the result (:222-224)
+        self.freq = fosc
+        self.fosc, self.Vosc = fosc, Vosc
+        self.osc_yosc = float(res.yosc[0])
+        print('Frequency of oscillation = {} Hz'.format(fosc))
+        print('Oscillation amplitude = {} V'.format(Vosc))
+        if not (res.converged[0] and res.hb_converged[0] > 0):
+            return False, None, None, None, None
+        self.freqs = res.freqs[0]
+        self.V = res.V[0].reshape(self.W, 1).copy()
+        self.Vf = res.Vf[0].copy()
+        return True, self.freqs, self.Vf, None, None
+
+    def _run_oscillator_fmin(self, netlist, f0, numharmonics, V0, node, useprev=False):
+        """The reference's own outer loop (:152-232): scipy.optimize.fmin on |Yosc| with its arguments; every
+        objective evaluation is one warm-started GPU solve."""
         from scipy import optimize
         netlist = netlist.copy()
         self.freq = f0
@@ -228,10 +256,12 @@ class MultiToneHarmonicBalance:
         print('Oscillation amplitude = {} V'.format(Vosc))
         return out
 
-    def run_oscillator_batch(self, netlist, f0, numharmonics, V0, node, sweeps=None, tol=1e-13, maxiter=30):
-        """Batched oscillator analysis without scipy.optimize: Newton on (fosc, Vosc) per oscillator, the probe
-        current taken from Kirchhoff's law at `node` (yalrf_b200/_osc.py).  f0 / V0: arrays of start points; sweeps
-        as in run_sweep.  Returns an object with fosc[B], Vosc[B], converged[B], yosc[B] (|Yosc| reached), Vf."""
+    def run_oscillator_batch(self, netlist, f0, numharmonics, V0, node, sweeps=None, tol=1e-12, maxiter=30):
+        """Batched oscillator analysis (start points, parameter sweeps: the reference's loops around run_oscillator,
+        tests/HBOscillators.ipynb:3052-3115) as ONE GPU call: yhb_oscillator_host, Newton on (fosc, Vosc) per
+        oscillator with the probe current from Kirchhoff's law at `node` and the exact 2 x 2 Jacobian.  f0 / V0:
+        arrays of start points; sweeps as in run_sweep.  Returns an object with fosc[B], Vosc[B], converged[B],
+        yosc[B] (|Yosc| reached), V, Vf, outer_iterations[B]."""
         from .. import _osc
         res = _osc.solve(self, netlist, f0, numharmonics, V0, node, sweeps=sweeps, tol=tol, maxiter=maxiter)
         self.netlist = res.netlist

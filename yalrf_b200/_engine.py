@@ -274,7 +274,13 @@ class DeviceBatch:
         lib = L.lib()
         st = (stream or torch.cuda.current_stream()).cuda_stream
         o = make_options(options)
-        if not have_v0 or with_dc:
+        if not have_v0 and not with_dc:
+            # cold start: DC analysis + ladder as one call (the DC kernel runs beside the HB kernel on the fused engine)
+            L.check(lib.yhb_solve_cold(self.plan.handle, C.byref(self.params), C.byref(o), self.ws.data_ptr(), self.ws_bytes,
+                                       self.Vdc.data_ptr(), self.dcinfo.data_ptr(), C.byref(self.result), st))
+            self.dc_done = True
+            return
+        if with_dc:
             L.check(lib.yhb_dc_solve(self.plan.handle, C.byref(self.params), self.ws.data_ptr(), self.ws_bytes,
                                      self.Vdc.data_ptr(), self.dcinfo.data_ptr(), st))
             self.dc_done = True

@@ -63,14 +63,34 @@ class Result(C.Structure):
         self.struct_size = C.sizeof(Result)
 
 
+class OscOptions(C.Structure):
+    """yhb_osc_options"""
+    _fields_ = [('struct_size', C.c_size_t), ('probe_src', C.c_int32), ('probe_filter', C.c_int32), ('node', C.c_int32),
+                ('max_outer', C.c_int32), ('tol', C.c_double), ('max_df_rel', C.c_double), ('max_dv_rel', C.c_double)]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.struct_size = C.sizeof(OscOptions)
+
+
+class OscResult(C.Structure):
+    """yhb_osc_result"""
+    _fields_ = [('struct_size', C.c_size_t), ('fosc', C.c_void_p), ('Vosc', C.c_void_p), ('yosc', C.c_void_p),
+                ('converged', C.c_void_p), ('outer_iters', C.c_void_p), ('hb_newton_iters', C.c_void_p), ('diag', C.c_void_p)]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.struct_size = C.sizeof(OscResult)
+
+
 _lib = None
 
 PROF_KINDS = ['prepare', 'dc', 'init', 'eval', 'assemble', 'lu', 'finish', 'fused']
 
 EXPORTS = ['yhb_last_error', 'yhb_version', 'yhb_set_device', 'yhb_profile_enable', 'yhb_profile_reset',
            'yhb_profile_read', 'yhb_fp64_peak', 'yhb_plan_create', 'yhb_plan_destroy',
-           'yhb_plan_dims', 'yhb_plan_core', 'yhb_plan_band', 'yhb_plan_engine', 'yhb_plan_block_sparse', 'yhb_plan_flops', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_newton',
-           'yhb_run_host', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu', 'yhb_stage_gj', 'yhb_stage_gjp', 'yhb_debug_timing']
+           'yhb_plan_dims', 'yhb_plan_core', 'yhb_plan_band', 'yhb_plan_engine', 'yhb_plan_block_sparse', 'yhb_plan_flops', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_solve_cold', 'yhb_newton',
+           'yhb_run_host', 'yhb_solve_oscillator', 'yhb_oscillator_host', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu', 'yhb_stage_gj', 'yhb_stage_gjp', 'yhb_debug_timing']
 
 
 def lib():
@@ -104,9 +124,15 @@ def lib():
                                C.c_void_p]
     L.yhb_solve.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.c_void_p, C.c_size_t, C.c_int32,
                             C.c_void_p, C.POINTER(Result), C.c_void_p]
+    L.yhb_solve_cold.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.c_void_p, C.c_size_t, C.c_void_p,
+                                 C.c_void_p, C.POINTER(Result), C.c_void_p]
     L.yhb_newton.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.c_void_p, C.c_size_t,
                              C.c_void_p, C.POINTER(Result), C.c_void_p]
     L.yhb_run_host.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.c_void_p, C.POINTER(Result)]
+    L.yhb_solve_oscillator.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.POINTER(OscOptions), C.c_void_p,
+                                       C.c_size_t, C.POINTER(Result), C.POINTER(OscResult), C.c_void_p]
+    L.yhb_oscillator_host.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.POINTER(OscOptions),
+                                      C.POINTER(Result), C.POINTER(OscResult)]
     L.yhb_stage_ifft.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.yhb_stage_device_eval.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]

@@ -17,6 +17,7 @@
 #include "yhb_dc.cuh"
 #include "yhb_dense.cuh"
 #include "yhb_kernels.cuh"
+#include "yhb_osc.cuh"
 
 namespace yhb {
 
@@ -187,6 +188,9 @@ struct yhb_plan : public yhb::Plan {
     size_t hbuf_bytes;
     std::mutex mu;
     std::vector<int> bs_host;  // block-sparse structure per core node: nlater, block rows below, 0, 0 (yhb_plan_flops)
+    // yhb_solve_cold: high-priority side stream of the DC kernel and the fork / join events
+    cudaStream_t dc_stream;
+    cudaEvent_t ev_fork, ev_join;
 };
 
 extern "C" const char *yhb_last_error(void) { return g_err.c_str(); }
@@ -830,6 +834,8 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     ok = ok && pl->lin_nodes_dev && pl->nl_kind_dev && pl->nl_index_dev;
     pl->pinned_counts = nullptr;
     pl->own_stream = nullptr;
+    pl->dc_stream = nullptr;
+    pl->ev_fork = pl->ev_join = nullptr;
     pl->hbuf = nullptr;
     pl->hbuf_bytes = 0;
     if (ok) ok = cudaHostAlloc((void **)&pl->pinned_counts, 4 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
@@ -848,6 +854,9 @@ extern "C" void yhb_plan_destroy(yhb_plan *pl) {
     if (pl->pinned_counts) cudaFreeHost(pl->pinned_counts);
     if (pl->hbuf) cudaFree(pl->hbuf);
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+    if (pl->dc_stream) cudaStreamDestroy(pl->dc_stream);
+    if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+    if (pl->ev_join) cudaEventDestroy(pl->ev_join);
     delete pl;
 }
 
@@ -958,7 +967,7 @@ int gjp_pivots(const PlanDev &d) {
     if (d.band > 0 || d.Wc < kGjpMinCore) return 0;
     return d.Wc;
 }
-int gjp_dense_ld(int Wc) { return (Wc + 2) & ~1; }  // [J | rhs | pad]: even and > Wc
+int gjp_dense_ld(int Wc) { return (gjp_npc(Wc) + 2) & ~1; }  // [J | pad to whole panels | rhs | pad]: even
 
 struct Layout {
     Workspace ws;
@@ -1009,6 +1018,9 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.gj_n = gjn;
     ws.gj_lpad = (gjn + 7) & ~7;
     ws.gj_L = c.take<double>(gjn ? (size_t)B * kGjpNB * ws.gj_lpad : 1);
+    ws.gj_ld = !gjn ? 0 : (d.btd ? btd_ldm(d.S) : gjp_dense_ld(d.Wc));
+    ws.gj_U = c.take<double>(gjn ? (size_t)B * kGjpNB * ws.gj_ld : 1);
+    ws.gj_T = c.take<double>((size_t)B * kGjpNB * kGjpNB);
     ws.gj_piv = c.take<double>(gjn ? (size_t)B * gjn : 1);
     ws.gj_rowof = c.take<int>(gjn ? (size_t)B * gjn : 1);
     ws.gj_used = c.take<int>(gjn ? (size_t)B * gjn : 1);
@@ -1016,6 +1028,17 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.gj_fail = c.take<int>(B);
     ws.Inl = nullptr;
     ws.Ic = nullptr;
+    ws.skip = nullptr;
+    ws.sens = nullptr;
+    ws.dylin = nullptr;
+    ws.sens_src_n1 = ws.sens_src_n2 = 0;
+    ws.osc_state = c.take<OscState>(B);
+    ws.osc_Vacc = c.take<double>(B * W);
+    ws.osc_Inl = c.take<double>(B * W);
+    ws.osc_sens = c.take<double>(2 * B * W);
+    ws.osc_dylin = c.take<double>((size_t)B * d.npair * K1);
+    ws.osc_skip = c.take<int>(B);
+    ws.osc_live = c.take<int>(4);
     ws.list[0] = c.take<int>(B);
     ws.list[1] = c.take<int>(B);
     ws.count = c.take<int>(4);
@@ -1026,6 +1049,11 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     const int M = d.N + pl->num_inductors;
     ws.dc_stride = dc_scratch_doubles(M, d.nd, d.nb, d.nc);
     ws.dcscratch = c.take<double>((size_t)B * ws.dc_stride);
+    ws.key = c.take<double>(B);
+    ws.order = c.take<int>(B);
+    ws.dc_ready = c.take<int>(B);
+    ws.use_order = 0;
+    ws.dc_wait = 0;
     L.dd = c.take<DiodeDerived>((size_t)B * std::max(d.nd, 1));
     L.bd = c.take<BjtDerived>((size_t)B * std::max(d.nb, 1));
     L.bytes = align_up(c.off);
@@ -1057,8 +1085,11 @@ int launch_prepare(const yhb_plan *pl, const yhb_params *p, const Layout &L, cud
     a.negbin = L.ws.negbin;
     a.dd = L.dd;
     a.bd = L.bd;
+    a.dylin = L.ws.dylin;
+    a.key = L.ws.use_order ? L.ws.key : nullptr;
     ProfScope ps(PK_PREPARE, st);
     k_prepare<<<p->batch, 128, 0, st>>>(pl->d, a, p->batch);
+    if (L.ws.use_order) k_order<<<(p->batch + 255) / 256, 256, 0, st>>>(L.ws.key, L.ws.order, p->batch);
     YHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1108,21 +1139,20 @@ int launch_finish(const yhb_plan *pl, Layout &L, const yhb_result *res, cudaStre
 // one DMMA trailing-update launch over the remaining columns.
 int gjp_run(const GjpBatch &g, int nsys, cudaStream_t st) {
     const int npanel = (g.n + kGjpNB - 1) / kGjpNB;
-    const int nt = std::min(1024, (g.n + 31) & ~31);
+    const int rpt = g.n <= 576 ? 1 : (g.n <= 1152 ? 2 : 0);  // rows per thread of the register panel kernel
     const size_t smem = (size_t)kGjpNB * (g.n | 1) * sizeof(double);
-    if (smem > 227 * 1024 - 1024) { set_error("panel Gauss-Jordan: more than 14 000 pivots per system"); return -4; }
-    if (smem > 48 * 1024)
-        YHB_CUDA(cudaFuncSetAttribute(k_gjp_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rpt == 0) {
+        if (smem > 227 * 1024 - 4096) { set_error("panel Gauss-Jordan: more than 14 000 pivots per system"); return -4; }
+        YHB_CUDA(cudaFuncSetAttribute(k_gjp_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int nrow_chunks = (g.n + kGjpUpdRows - 1) / kGjpUpdRows;
     for (int j = 0; j < npanel; ++j) {
-        k_gjp_panel<<<nsys, nt, smem, st>>>(g, j);
+        if (rpt == 1) k_gjp_panel<1><<<nsys, (g.n + 31) & ~31, 0, st>>>(g, j);
+        else if (rpt == 2) k_gjp_panel<2><<<nsys, ((g.n + 1) / 2 + 31) & ~31, 0, st>>>(g, j);
+        else k_gjp_panel_smem<<<nsys, 1024, smem, st>>>(g, j);
         const int rem = g.ncols - (j + 1) * kGjpNB;
         if (rem <= 0) continue;
-        // wide column chunks once there are enough CTAs to fill the GPU several times over
-        if ((long)((rem + 15) / 16) * nsys >= 1200) {
-            k_gjp_update<32><<<dim3((rem + 31) / 32, nsys), 256, 0, st>>>(g, j);
-        } else {
-            k_gjp_update<16><<<dim3((rem + 15) / 16, nsys), 256, 0, st>>>(g, j);
-        }
+        k_gjp_update<<<dim3((rem + kGjpUpdCols - 1) / kGjpUpdCols, nrow_chunks, nsys), 256, 0, st>>>(g, j);
     }
     YHB_CUDA(cudaGetLastError());
     return 0;
@@ -1134,6 +1164,8 @@ GjpBatch gjp_batch(const Workspace &ws, const int *list) {
     g.M = ws.J;
     g.m_stride = ws.j_stride;
     g.L = ws.gj_L;
+    g.U = ws.gj_U;
+    g.T = ws.gj_T;
     g.piv = ws.gj_piv;
     g.rowof = ws.gj_rowof;
     g.used = ws.gj_used;
@@ -1156,7 +1188,7 @@ int block_thomas_solve(const PlanDev &d, const Workspace &ws, const int *list, i
     const int S = d.S, Nc = d.Nc;
     GjpBatch g = gjp_batch(ws, list);
     g.ld = btd_ldm(S);
-    g.ncols = 2 * S + 1;
+    g.ncols = gjp_npc(S) + S + 1;
     SchurArgs sa;
     sa.J = ws.J;
     sa.j_stride = ws.j_stride;
@@ -1196,19 +1228,97 @@ int block_thomas_solve(const PlanDev &d, const Workspace &ws, const int *list, i
     return 0;
 }
 
+// calc_V0 (:697-704) = DC.run (DC.py:54-123) for the batch.  order / ready: see DcArgs (overlap with the HB kernel).
+int dc_launch(const yhb_plan *pl, const yhb_params *p, const Layout &L, double *Vdc, int32_t *dc_info, const int *order,
+              int *ready, cudaStream_t st) {
+    const PlanDev &d = pl->d;
+    DcArgs a;
+    a.lin_val = p->lin_val;
+    a.src_val = p->src_val;
+    a.diode_par = p->diode_par;
+    a.bjt_par = p->bjt_par;
+    a.cubic_par = p->cubic_par;
+    a.lin_nodes = pl->lin_nodes_dev;
+    a.nl_kind = pl->nl_kind_dev;
+    a.nl_index = pl->nl_index_dev;
+    a.nnl = d.nd + d.nb + d.nc;
+    a.M = d.N + pl->num_inductors;
+    a.scratch = L.ws.dcscratch;
+    a.stride = L.ws.dc_stride;
+    a.Vdc = Vdc ? Vdc : L.ws.dcV;
+    a.info = dc_info ? dc_info : L.ws.dcinfo;
+    a.ent_tab = pl->dc_ent_dev;
+    a.ent_ints = pl->dc_ent_ints;
+    a.lane_tab = pl->dc_lane_dev;
+    a.order = order;
+    a.ready = ready;
+    a.use_smem = 0;
+    // YHB_DC_ENGINE=block forces the general engine (A/B runs, parity tests of the one-warp engine against it)
+    const char *dc_env = getenv("YHB_DC_ENGINE");  // read per call: tests flip it within one process
+    const bool force_block = dc_env && !strcmp(dc_env, "block");
+    if (pl->dc_warp && !force_block) {
+        const int LD = (a.M + 1) | 1;
+        const size_t smw = ((size_t)a.M * a.M + a.M + (size_t)kDcOut * std::max(a.nnl, 1) + (size_t)a.M * LD) * sizeof(double) +
+                           (size_t)a.ent_ints * sizeof(int);
+        ProfScope ps(PK_DC, st);
+        if (a.M <= 12) k_dc_warp<12><<<p->batch, 32, smw, st>>>(d, a, p->batch);
+        else k_dc_warp<24><<<p->batch, 32, smw, st>>>(d, a, p->batch);
+        YHB_CUDA(cudaGetLastError());
+        return 0;
+    }
+    size_t dsm = (a.M + 2) * sizeof(double);
+    a.use_smem = (dsm + a.stride * sizeof(double)) <= 40 * 1024;  // small circuits: the whole DC analysis on chip
+    if (a.use_smem) dsm += a.stride * sizeof(double);
+    {
+        ProfScope ps(PK_DC, st);
+        k_dc<<<p->batch, kDcThreads, dsm, st>>>(d, a, p->batch);
+    }
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// DC analysis to run beside the fused HB kernel (yhb_solve_cold): outputs of the DC kernel
+struct DcOverlap {
+    double *Vdc;
+    int32_t *info;
+};
+
 // the Newton / continuation launch loop shared by yhb_solve and yhb_newton
+// dco (fused engine, cold start only): the DC analysis runs on the plan's high-priority side stream BESIDE the HB
+// kernel, which takes the circuits in the DC kernel's order and waits for each operating point (ws.dc_wait)
 int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, Layout &L, int have_v0,
-             const double *alpha_fixed, const yhb_result *res, cudaStream_t st) {
-    const yhb_plan *pl = cpl;
+             const double *alpha_fixed, const yhb_result *res, cudaStream_t st, const DcOverlap *dco = nullptr) {
+    yhb_plan *pl = const_cast<yhb_plan *>(cpl);  // side stream and events are created on first use
     const PlanDev &d = pl->d;
     const int B = p->batch;
     Workspace &ws = L.ws;
+    if (dco) {
+        if (!L.fused || have_v0) { set_error("internal: DC overlap needs the fused engine and a cold start"); return -4; }
+        if (!pl->dc_stream) {
+            int lo = 0, hi = 0;
+            YHB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            YHB_CUDA(cudaStreamCreateWithPriority(&pl->dc_stream, cudaStreamNonBlocking, hi));
+            YHB_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+            YHB_CUDA(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+        }
+        ws.use_order = 1;
+        ws.dc_wait = 1;
+        ws.dc_valid = 1;
+        if (dco->Vdc) ws.dcV = dco->Vdc;
+        YHB_CUDA(cudaMemsetAsync(ws.dc_ready, 0, sizeof(int) * (size_t)B, st));
+    }
     if (int rc = launch_prepare(pl, p, L, st)) return rc;
     {
         ProfScope ps(PK_INIT, st);
         k_init<<<B, 128, 0, st>>>(d, ws, have_v0, alpha_fixed);
     }
     YHB_CUDA(cudaGetLastError());
+    if (dco) {  // fork: the DC kernel is launched FIRST, on the high-priority stream, in the HB kernel's work order
+        YHB_CUDA(cudaEventRecord(pl->ev_fork, st));
+        YHB_CUDA(cudaStreamWaitEvent(pl->dc_stream, pl->ev_fork, 0));
+        if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, ws.order, ws.dc_ready, pl->dc_stream)) return rc;
+        YHB_CUDA(cudaEventRecord(pl->ev_join, pl->dc_stream));
+    }
     EvalArgs ea = eval_args(pl, p, opt, L);
     if (L.fused) {
         const int fsmem = (int)L.fc.smem;
@@ -1234,6 +1344,7 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
         }
 #undef YHB_LAUNCH_FUSED
         YHB_CUDA(cudaGetLastError());
+        if (dco) YHB_CUDA(cudaStreamWaitEvent(st, pl->ev_join, 0));  // join: Vdc / dc_info are complete for the caller
         return launch_finish(pl, L, res, st);
     }
     const int smem = eval_smem_bytes(pl, L);
@@ -1277,7 +1388,7 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
                 } else {
                     GjpBatch g = gjp_batch(ws, ws.list[cur ^ 1]);
                     g.ld = gjp_dense_ld(d.Wc);
-                    g.ncols = d.Wc + 1;
+                    g.ncols = gjp_npc(d.Wc) + 1;
                     if (int rc = gjp_run(g, nsolve, st)) return rc;
                     GjpFinish f;
                     memset(&f, 0, sizeof(f));
@@ -1323,61 +1434,20 @@ extern "C" int yhb_dc_solve(const yhb_plan *pl, const yhb_params *p, void *wsbuf
     if (int rc = check_params(pl, p)) return rc;
     Layout L = carve(pl, p->batch, wsbuf);
     if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
-    const PlanDev &d = pl->d;
-    DcArgs a;
-    a.lin_val = p->lin_val;
-    a.src_val = p->src_val;
-    a.diode_par = p->diode_par;
-    a.bjt_par = p->bjt_par;
-    a.cubic_par = p->cubic_par;
-    a.lin_nodes = pl->lin_nodes_dev;
-    a.nl_kind = pl->nl_kind_dev;
-    a.nl_index = pl->nl_index_dev;
-    a.nnl = d.nd + d.nb + d.nc;
-    a.M = d.N + pl->num_inductors;
-    a.scratch = L.ws.dcscratch;
-    a.stride = L.ws.dc_stride;
-    a.Vdc = Vdc ? Vdc : L.ws.dcV;
-    a.info = dc_info ? dc_info : L.ws.dcinfo;
-    a.ent_tab = pl->dc_ent_dev;
-    a.ent_ints = pl->dc_ent_ints;
-    a.lane_tab = pl->dc_lane_dev;
-    cudaStream_t st = (cudaStream_t)stream;
-    // YHB_DC_ENGINE=block forces the general engine (A/B runs, parity tests of the one-warp engine against it)
-    const char *dc_env = getenv("YHB_DC_ENGINE");  // read per call: tests flip it within one process
-    const bool force_block = dc_env && !strcmp(dc_env, "block");
-    if (pl->dc_warp && !force_block) {
-        const int LD = (a.M + 1) | 1;
-        const size_t smw = ((size_t)a.M * a.M + a.M + (size_t)kDcOut * std::max(a.nnl, 1) + (size_t)a.M * LD) * sizeof(double) +
-                           (size_t)a.ent_ints * sizeof(int);
-        ProfScope ps(PK_DC, st);
-        if (a.M <= 12) k_dc_warp<12><<<p->batch, 32, smw, st>>>(d, a, p->batch);
-        else k_dc_warp<24><<<p->batch, 32, smw, st>>>(d, a, p->batch);
-        YHB_CUDA(cudaGetLastError());
-        return 0;
-    }
-    size_t dsm = (a.M + 2) * sizeof(double);
-    a.use_smem = (dsm + a.stride * sizeof(double)) <= 40 * 1024;  // small circuits: the whole DC analysis on chip
-    if (a.use_smem) dsm += a.stride * sizeof(double);
-    {
-        ProfScope ps(PK_DC, st);
-        k_dc<<<p->batch, kDcThreads, dsm, st>>>(d, a, p->batch);
-    }
-    YHB_CUDA(cudaGetLastError());
-    return 0;
+    return dc_launch(pl, p, L, Vdc, dc_info, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // lock = false: the caller (yhb_run_host) already holds pl->mu
 static int solve_common(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
                         size_t ws_bytes, int have_v0, const double *Vdc, const double *alpha,
-                        const yhb_result *res_in, void *stream, bool lock) {
+                        const yhb_result *res_in, void *stream, bool lock, const DcOverlap *dco = nullptr) {
     if (int rc = check_params(pl, p)) return rc;
     yhb_result R;
     if (int rc = load_result(res_in, R)) return rc;
     Layout L = carve(pl, p->batch, wsbuf);
     if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
     if (have_v0 && !R.V) { set_error("have_v0 set but res->V is null"); return -1; }
-    if (!have_v0 && !Vdc) { set_error("cold start needs Vdc"); return -1; }
+    if (!have_v0 && !Vdc && !dco) { set_error("cold start needs Vdc"); return -1; }
     if (R.V) L.ws.V = R.V;
     L.ws.Inl = R.Inl;
     L.ws.Ic = R.Ic;
@@ -1385,7 +1455,28 @@ static int solve_common(const yhb_plan *pl, const yhb_params *p, const yhb_optio
     L.ws.dc_valid = Vdc != nullptr;
     std::unique_lock<std::mutex> lk(const_cast<yhb_plan *>(pl)->mu, std::defer_lock);  // pinned counters are per plan
     if (lock) lk.lock();
-    return run_loop(pl, p, opt, L, have_v0, alpha, &R, (cudaStream_t)stream);
+    return run_loop(pl, p, opt, L, have_v0, alpha, &R, (cudaStream_t)stream, dco);
+}
+
+// calc_V0 + run() for cold starts (:321-324, :338-384) as ONE call.  Fused engine: the DC kernel runs beside the HB
+// kernel (side stream, per-circuit ready flags) instead of in front of it; staged engines: DC, then the solve.
+static int solve_cold(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf, size_t ws_bytes,
+                      double *Vdc, int32_t *dc_info, const yhb_result *res, void *stream, bool lock) {
+    if (int rc = check_params(pl, p)) return rc;
+    Layout L = carve(pl, p->batch, wsbuf);
+    if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
+    static const bool no_overlap = getenv("YHB_NO_DC_OVERLAP") != nullptr;  // A/B runs
+    if (L.fused && !no_overlap) {
+        DcOverlap dco{Vdc ? Vdc : L.ws.dcV, dc_info ? dc_info : L.ws.dcinfo};
+        return solve_common(pl, p, opt, wsbuf, ws_bytes, 0, nullptr, nullptr, res, stream, lock, &dco);
+    }
+    if (int rc = dc_launch(pl, p, L, Vdc, dc_info, nullptr, nullptr, (cudaStream_t)stream)) return rc;
+    return solve_common(pl, p, opt, wsbuf, ws_bytes, 0, Vdc ? Vdc : L.ws.dcV, nullptr, res, stream, lock);
+}
+
+extern "C" int yhb_solve_cold(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
+                              size_t ws_bytes, double *Vdc, int32_t *dc_info, const yhb_result *res, void *stream) {
+    return solve_cold(pl, p, opt, wsbuf, ws_bytes, Vdc, dc_info, res, stream, true);
 }
 
 extern "C" int yhb_solve(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt, void *wsbuf,
@@ -1515,9 +1606,8 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
     if (int rc = h2d_params(pl, hp, dp, st)) return rc;
     if (V0) YHB_CUDA(cudaMemcpyAsync(dr.V, V0, B * W * sizeof(double), cudaMemcpyHostToDevice, st));
     Layout L = carve(pl, (int)B, wsb);
-    if (!V0) {  // cold start: DC operating points first (calc_V0, :321-322)
-        if (int rc = yhb_dc_solve(pl, &dp, wsb, wsbytes, nullptr, nullptr, st)) return rc;
-        if (int rc = solve_common(pl, &dp, opt, wsb, wsbytes, 0, L.ws.dcV, nullptr, &dr, st, false)) return rc;
+    if (!V0) {  // cold start: DC operating points (calc_V0, :321-322) beside / before the ladder
+        if (int rc = solve_cold(pl, &dp, opt, wsb, wsbytes, nullptr, nullptr, &dr, st, false)) return rc;
     } else {
         // warm start: the DC analysis is only needed if a direct attempt fails (:333-335); such circuits come
         // back with converged = -1 and the batch is re-run from the same V0 with the DC points available
@@ -1536,6 +1626,175 @@ extern "C" int yhb_run_host(const yhb_plan *cpl, const yhb_params *hp, const yhb
     if (int rc = d2h_result(pl, B, hr, dr, st)) return rc;
     YHB_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+// ---- autonomous oscillators (run_oscillator, :137-232) ------------------------------------------------
+namespace {
+int load_osc(const yhb_osc_options *in, yhb_osc_options &o, const yhb_osc_result *rin, yhb_osc_result &r) {
+    memset(&o, 0, sizeof(o));
+    memset(&r, 0, sizeof(r));
+    if (!in || !rin) { set_error("null oscillator options / result"); return -1; }
+    if (in->struct_size < 4 * sizeof(int32_t) + sizeof(size_t) || in->struct_size > 4096 ||
+        rin->struct_size < sizeof(size_t) + 2 * sizeof(void *) || rin->struct_size > 4096) {
+        set_error("yhb_osc_options / yhb_osc_result: struct_size not set");
+        return -1;
+    }
+    memcpy(&o, in, std::min((size_t)in->struct_size, sizeof(o)));
+    memcpy(&r, rin, std::min((size_t)rin->struct_size, sizeof(r)));
+    if (o.max_outer <= 0) o.max_outer = 30;
+    if (!(o.tol > 0)) o.tol = 1e-12;          // the reference stops at |Yosc| < 1e-12 (:191)
+    if (!(o.max_df_rel > 0)) o.max_df_rel = 0.02;
+    if (!(o.max_dv_rel > 0)) o.max_dv_rel = 0.3;
+    return 0;
+}
+
+// device part of the oscillator solve; the caller holds pl->mu.  dp's tones / lin_val / src_val are rewritten.
+int osc_run(const yhb_plan *pl, const yhb_params *dp, const yhb_options *opt, const yhb_osc_options &oo, void *wsbuf,
+            size_t ws_bytes, const yhb_result &R, const yhb_osc_result &dor, cudaStream_t st, int32_t *iterations) {
+    const PlanDev &d = pl->d;
+    const int B = dp->batch;
+    if (d.ntones != 1) { set_error("oscillator solve: single-tone analyses only (as run_oscillator, :137)"); return -1; }
+    if (oo.probe_src < 0 || oo.probe_src >= d.nsrc || oo.probe_filter < 0 || oo.probe_filter >= d.nlin ||
+        oo.node < 1 || oo.node > d.N || pl->lin_kind[oo.probe_filter] != YHB_LIN_IHF ||
+        pl->src_kind[oo.probe_src] != YHB_SRC_AC1) {
+        set_error("oscillator solve: probe_src must be an AC source at the tone, probe_filter an IdealHarmonicFilter, "
+                  "node a non-ground node");
+        return -1;
+    }
+    const int fn1 = pl->lin_nodes[4 * oo.probe_filter], fn2 = pl->lin_nodes[4 * oo.probe_filter + 1];
+    if (fn1 != oo.node && fn2 != oo.node) { set_error("oscillator solve: the probe filter is not connected to node"); return -1; }
+    if (!dor.fosc || !dor.Vosc) { set_error("oscillator solve: fosc / Vosc (start point in, result out) are required"); return -1; }
+    Layout L = carve(pl, B, wsbuf);
+    if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
+    if (!L.fused) { set_error("oscillator solve: the circuit does not fit the on-chip engine"); return -4; }
+    Workspace &ws = L.ws;
+    if (R.V) ws.V = R.V;
+    ws.Inl = ws.osc_Inl;
+    ws.Ic = R.Ic;
+    ws.sens = ws.osc_sens;
+    ws.dylin = ws.osc_dylin;
+    ws.skip = ws.osc_skip;
+    ws.sens_src_n1 = pl->src_nodes[2 * oo.probe_src];
+    ws.sens_src_n2 = pl->src_nodes[2 * oo.probe_src + 1];
+    ws.dc_valid = 1;
+    OscArgs a;
+    a.st = reinterpret_cast<OscState *>(ws.osc_state);
+    a.tones = const_cast<double *>(dp->tones);
+    a.lin_val = const_cast<double *>(dp->lin_val);
+    a.src_val = const_cast<double *>(dp->src_val);
+    a.V = ws.V;
+    a.Vacc = ws.osc_Vacc;
+    a.Inl = ws.osc_Inl;
+    a.sens = ws.osc_sens;
+    a.ctl = ws.ctl;
+    a.skip = ws.osc_skip;
+    a.live = ws.osc_live;
+    a.probe_src = oo.probe_src;
+    a.probe_filter = oo.probe_filter;
+    a.node = oo.node;
+    a.nosc2 = fn1 == oo.node ? fn2 : fn1;
+    a.tol = oo.tol;
+    a.max_df_rel = oo.max_df_rel;
+    a.max_da_rel = oo.max_dv_rel;
+    a.B = B;
+    k_osc_begin<<<(B + 127) / 128, 128, 0, st>>>(a, dor.fosc, dor.Vosc);
+    YHB_CUDA(cudaGetLastError());
+    // calc_V0: the DC point does not depend on the probe (AC source, filter: 1e-12 S at DC)
+    if (int rc = yhb_dc_solve(pl, dp, wsbuf, ws_bytes, ws.dcV, ws.dcinfo, st)) return rc;
+    int *hc = pl->pinned_counts;
+    int it = 0;
+    for (; it < oo.max_outer; ++it) {
+        k_osc_set<<<B, 128, 0, st>>>(d, a);
+        YHB_CUDA(cudaMemsetAsync(ws.osc_live, 0, sizeof(int), st));
+        // first pass: cold start of every oscillator (run(netlist), :171); afterwards warm starts from the accepted
+        // point (run(netlist, self.V), :166), the DC point at hand for a failed direct attempt (:333-335)
+        if (int rc = run_loop(pl, dp, opt, L, it > 0, nullptr, &R, st)) return rc;
+        k_osc_update<<<B, 128, 0, st>>>(d, a);
+        YHB_CUDA(cudaGetLastError());
+        YHB_CUDA(cudaMemcpyAsync(hc, ws.osc_live, sizeof(int), cudaMemcpyDeviceToHost, st));
+        YHB_CUDA(cudaStreamSynchronize(st));
+        if (hc[0] == 0) { ++it; break; }
+    }
+    if (iterations) *iterations = it;
+    OscOut o;
+    o.fosc = dor.fosc;
+    o.Vosc = dor.Vosc;
+    o.yosc = dor.yosc;
+    o.converged = dor.converged;
+    o.outer_iters = dor.outer_iters;
+    o.hb_newton_iters = dor.hb_newton_iters;
+    o.diag = dor.diag;
+    k_osc_finish<<<B, 128, 0, st>>>(d, a, o);
+    YHB_CUDA(cudaGetLastError());
+    ws.skip = nullptr;  // phasors of the accepted points for every oscillator
+    return launch_finish(pl, L, &R, st);
+}
+}  // namespace
+
+extern "C" int yhb_solve_oscillator(const yhb_plan *pl, const yhb_params *p, const yhb_options *opt,
+                                    const yhb_osc_options *osc, void *wsbuf, size_t ws_bytes, const yhb_result *res,
+                                    const yhb_osc_result *ores, void *stream) {
+    if (int rc = check_params(pl, p)) return rc;
+    yhb_result R;
+    if (int rc = load_result(res, R)) return rc;
+    yhb_osc_options oo;
+    yhb_osc_result dor;
+    if (int rc = load_osc(osc, oo, ores, dor)) return rc;
+    std::lock_guard<std::mutex> lk(const_cast<yhb_plan *>(pl)->mu);
+    return osc_run(pl, p, opt, oo, wsbuf, ws_bytes, R, dor, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int yhb_oscillator_host(const yhb_plan *cpl, const yhb_params *hp, const yhb_options *opt,
+                                   const yhb_osc_options *osc, const yhb_result *hr_in, const yhb_osc_result *hor_in) {
+    yhb_plan *pl = const_cast<yhb_plan *>(cpl);
+    if (int rc = check_params(pl, hp)) return rc;
+    yhb_result hr;
+    if (int rc = load_result(hr_in, hr)) return rc;
+    yhb_osc_options oo;
+    yhb_osc_result hor;
+    if (int rc = load_osc(osc, oo, hor_in, hor)) return rc;
+    if (!hor.fosc || !hor.Vosc) { set_error("oscillator solve: fosc / Vosc (start point in, result out) are required"); return -1; }
+    std::lock_guard<std::mutex> lk(pl->mu);
+    const size_t B = hp->batch;
+    HostStage hs;
+    if (int rc = stage_host(pl, B, hr, hs)) return rc;
+    cudaStream_t st = pl->own_stream;
+    if (int rc = h2d_params(pl, hp, hs.dp, st)) return rc;
+    // oscillator results: one small device block [fosc | Vosc | yosc (2) | converged, outer, newton (ints)]
+    double *dblk = nullptr;
+    YHB_CUDA(cudaMalloc(&dblk, B * (20 * sizeof(double) + 4 * sizeof(int32_t))));
+    yhb_osc_result dor;
+    memset(&dor, 0, sizeof(dor));
+    dor.struct_size = sizeof(dor);
+    dor.fosc = dblk;
+    dor.Vosc = dblk + B;
+    dor.yosc = dblk + 2 * B;
+    dor.diag = dblk + 4 * B;
+    int32_t *iblk = reinterpret_cast<int32_t *>(dblk + 20 * B);
+    dor.converged = iblk;
+    dor.outer_iters = iblk + B;
+    dor.hb_newton_iters = iblk + 2 * B;
+    int rc = 0;
+    auto cp = [&](void *dst, const void *src, size_t bytes, cudaMemcpyKind k) {
+        if (rc == 0 && dst && src && cudaMemcpyAsync(dst, src, bytes, k, st) != cudaSuccess) {
+            set_error("oscillator solve: copy failed");
+            rc = -2;
+        }
+    };
+    cp(dor.fosc, hor.fosc, B * sizeof(double), cudaMemcpyHostToDevice);
+    cp(dor.Vosc, hor.Vosc, B * sizeof(double), cudaMemcpyHostToDevice);
+    if (rc == 0) rc = osc_run(pl, &hs.dp, opt, oo, hs.wsb, hs.wsbytes, hs.dr, dor, st, nullptr);
+    if (rc == 0) rc = d2h_result(pl, B, hr, hs.dr, st);
+    cp(hor.fosc, dor.fosc, B * sizeof(double), cudaMemcpyDeviceToHost);
+    cp(hor.Vosc, dor.Vosc, B * sizeof(double), cudaMemcpyDeviceToHost);
+    cp(hor.yosc, dor.yosc, 2 * B * sizeof(double), cudaMemcpyDeviceToHost);
+    cp(hor.diag, dor.diag, 16 * B * sizeof(double), cudaMemcpyDeviceToHost);
+    cp(hor.converged, dor.converged, B * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cp(hor.outer_iters, dor.outer_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cp(hor.hb_newton_iters, dor.hb_newton_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaStreamSynchronize(st);
+    cudaFree(dblk);
+    return rc;
 }
 
 // ---- stage entry points -----------------------------------------------------------------------------
@@ -1710,8 +1969,9 @@ __global__ void k_gjp_pack(int n, int nrhs, int ld, const double *A, const doubl
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * ld; e += gridDim.x * blockDim.x) {
         const int r = e / ld, c = e - r * ld;
         double v = 0.;
+        const int npc = gjp_npc(n);
         if (c < n) v = A[(b * n + r) * n + c];
-        else if (c < n + nrhs) v = Bm[(b * n + r) * nrhs + (c - n)];
+        else if (c >= npc && c < npc + nrhs) v = Bm[(b * n + r) * nrhs + (c - npc)];
         M[b * (size_t)n * ld + e] = v;
     }
 }
@@ -1721,11 +1981,13 @@ extern "C" int yhb_stage_gjp(int32_t batch, int32_t n, int32_t nrhs, const doubl
                              void *stream) {
     if (batch < 1 || n < 1 || nrhs < 1 || !A || !Bm || !X) { set_error("bad argument"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int ld = (n + nrhs + 2) & ~1, lpad = (n + 7) & ~7;
+    const int npc = gjp_npc(n), ld = (npc + nrhs + 2) & ~1, lpad = (n + 7) & ~7;
     Carver c{nullptr, 0};
     auto carve_all = [&](Carver &cv, GjpBatch &g) {
         g.M = cv.take<double>((size_t)batch * n * ld);
         g.L = cv.take<double>((size_t)batch * kGjpNB * lpad);
+        g.U = cv.take<double>((size_t)batch * kGjpNB * ld);
+        g.T = cv.take<double>((size_t)batch * kGjpNB * kGjpNB);
         g.piv = cv.take<double>((size_t)batch * n);
         g.rowof = cv.take<int>((size_t)batch * n);
         g.used = cv.take<int>((size_t)batch * n);
@@ -1742,7 +2004,7 @@ extern "C" int yhb_stage_gjp(int32_t batch, int32_t n, int32_t nrhs, const doubl
     g.m_stride = (size_t)n * ld;
     g.n = n;
     g.ld = ld;
-    g.ncols = n + nrhs;
+    g.ncols = npc + nrhs;
     g.lpad = lpad;
     k_gjp_pack<<<dim3(std::max(1, std::min(256, n * ld / 256)), batch), 256, 0, st>>>(n, nrhs, ld, A, Bm, g.M);
     int rc = gjp_run(g, batch, st);

@@ -40,6 +40,10 @@ struct DcArgs {
                            // [items] contributions in stamping order: ((t * kDcOut + slot) << 1) | negate
     int ent_ints;
     const int *lane_tab;   // [32][kDcLaneInts] role of every lane in the device evaluation
+    // DC analysis overlapped with the harmonic-balance kernel (yhb_solve_cold): CTA i takes circuit order[i] (the order
+    // in which the HB kernel will ask for them) and publishes ready[b] = 1 once Vdc[b] is in memory
+    const int *order;      // [B] or nullptr
+    int *ready;            // [B] or nullptr
 };
 
 constexpr int kDcOut = 12;
@@ -364,8 +368,8 @@ __global__ void __launch_bounds__(kDcThreads) k_dc(PlanDev P, DcArgs a, int batc
     __shared__ double s_val[32];
     __shared__ int s_idx[33];
     __shared__ int s_flag;
-    const int b = blockIdx.x;
-    if (b >= batch) return;
+    if ((int)blockIdx.x >= batch) return;
+    const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
     const int M = a.M, N = P.N, tid = threadIdx.x, nt = blockDim.x;
     DcCtx c;
     c.P = &P;
@@ -472,6 +476,11 @@ __global__ void __launch_bounds__(kDcThreads) k_dc(PlanDev P, DcArgs a, int batc
     if (tid == 0 && a.info) {
         a.info[2 * b] = solved ? 1 : 0;
         a.info[2 * b + 1] = c.newton;
+    }
+    if (a.ready) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicExch(a.ready + b, 1);
     }
 }
 
@@ -735,8 +744,8 @@ template <int MMAX>
 #endif
 __global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P, DcArgs a, int batch) {
     extern __shared__ double smw[];
-    const int b = blockIdx.x;
-    if (b >= batch) return;
+    if ((int)blockIdx.x >= batch) return;
+    const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
     const int M = a.M, N = P.N, lane = threadIdx.x;
     DcWarp<MMAX> w;
     w.M = M;
@@ -864,6 +873,11 @@ __global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P
     if (lane == 0 && a.info) {
         a.info[2 * b] = solved ? 1 : 0;
         a.info[2 * b + 1] = w.newton;
+    }
+    if (a.ready) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(a.ready + b, 1);
     }
 }
 

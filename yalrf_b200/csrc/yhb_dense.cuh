@@ -5,16 +5,18 @@
 //   * the block-Thomas engine      (config 5: per block row one system [D_i | U_i | b_i] of S = 1089 pivots with
 //                                   S + 1 carried columns, then the Schur complement of the next block row),
 // which round 1 ran as cuBLAS / cuSOLVER calls from a host loop.  Per panel two launches:
-//   k_gjp_panel   one CTA per system holds the panel's 16 columns of all n rows in shared memory (column-major) and
-//                 factors them: per column ONE barrier -- warp arg-max by redux on the bit pattern of |a| (first row of
-//                 maximal |a| among the rows not yet used: the idamax rule of dgetrf), cross-warp vote through shared
-//                 memory re-reduced by every warp, multipliers l = -(a * (1 / pivot)) as dgetf2 scales them, in-panel
-//                 update of the thread's own rows.  Rows are never moved (implicit pivoting) and rows above the
-//                 pivot are eliminated too (Gauss-Jordan: no triangular solves, full-height rank-16 updates).
-//   k_gjp_update  every CTA owns 16 (or 32) of the remaining columns for ALL rows: stages the 16 pivot rows of its
-//                 columns, completes them (row s is still subject to the panel's earlier pivots), and applies
-//                 A += L (n x 16) . U (16 x cols) with FP64 tensor-core instructions (mma.sync.m8n8k4.f64, DMMA):
-//                 the trailing-update contraction, the only place the tensor pipe is used, as BASELINE.json asks.
+//   k_gjp_panel   one CTA per system factors the panel's 16 columns of all n rows, rows in registers (up to 1152
+//                 rows; a shared-memory variant takes more): per column a vote -- warp arg-max by redux on the bit
+//                 pattern of |a| (first row of maximal |a| among the rows not yet used: the idamax rule of dgetrf),
+//                 cross-warp through shared memory, re-reduced by every warp -- the pivot row published by its owner,
+//                 multipliers l = -(a * (1 / pivot)) as dgetf2 scales them, in-panel update of the thread's own rows.
+//                 Rows are never moved (implicit pivoting) and rows above the pivot are eliminated too (Gauss-Jordan:
+//                 no triangular solves, full-height rank-16 updates).  Its tail snapshots the 16 pivot rows for the
+//                 trailing columns into a separate buffer U.
+//   k_gjp_update  CTAs of 128 rows x 32 columns complete their columns of U (row s is still subject to the panel's
+//                 earlier pivots) and apply A += L (n x 16) . U (16 x cols) with FP64 tensor-core instructions
+//                 (mma.sync.m8n8k4.f64, DMMA): the trailing-update contraction, the only place the tensor pipe is
+//                 used, as BASELINE.json asks.
 // k_gjp_finish scales the carried columns by the pivots and un-permutes them; k_btd_schur is the DMMA GEMM
 // D_{i+1} -= L_{i+1} U'_i (shared-memory tiles, cp.async double buffering); k_btd_back the back substitution.
 #pragma once
@@ -23,6 +25,9 @@
 namespace yhb {
 
 constexpr int kGjpNB = 16;  // pivot columns per panel
+// first carried column of a system of n pivots: the pivot columns are padded to whole panels, so that the trailing
+// update of a panel (columns >= 16 (j + 1)) covers every carried column also for the last, partial panel
+__host__ __device__ inline int gjp_npc(int n) { return (n + kGjpNB - 1) & ~(kGjpNB - 1); }
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -32,9 +37,12 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 
 // A batch of systems under elimination.  System index: pos = blockIdx -> s = list ? list[pos] : pos (active circuits).
 struct GjpBatch {
-    double *M;        // working matrices, system s at M + s * m_stride (+ m_off), [n][ld] row-major: [A | carried]
+    double *M;        // working matrices, system s at M + s * m_stride (+ m_off), [n][ld] row-major:
+                      // [A (n columns) | pad to gjp_npc(n) | carried columns], ncols = gjp_npc(n) + carried
     size_t m_stride, m_off;
     double *L;        // multipliers of the current panel, system s at L + s * kGjpNB * lpad: [16][lpad]
+    double *U;        // snapshot of the pivot rows of the current panel, system s at U + s * kGjpNB * ld: [16][ld]
+    double *T;        // [16][16] per system: T[s][s'] = l_{s'}[p_s], s' < s
     double *piv;      // [n] per system (stride n): pivot value of every column
     int *rowof;       // [n] per system: row that eliminated column c (-1: no admissible pivot)
     int *used;        // [n] per system: row has been a pivot row
@@ -62,11 +70,153 @@ __device__ __forceinline__ void gjp_warp_best(unsigned &hi, unsigned &lo, int &r
     row = mhi != 0u ? (int)r : -1;
 }
 
-// Panel j (columns 16 j .. 16 j + 15 of A) of every system.  Dynamic shared memory: 16 * npad doubles, npad = n | 1.
-__global__ void __launch_bounds__(1024) k_gjp_panel(GjpBatch g, int j) {
-    extern __shared__ double P[];  // [16][npad] column-major panel; column s holds its multipliers once it is eliminated
+// Tail of a panel factorisation, by the panel's CTA after its last column: a SNAPSHOT of the 16 pivot rows for the
+// columns right of the panel, U[s][c] = M[p_s][c] (the update kernel's CTAs split the rows among themselves, and all of
+// them read the pivot rows that some of them overwrite), and the 16 x 16 table T[s][s'] = l_{s'}[p_s], s' < s: what
+// pivot row s still owes to the panel's earlier pivots.  The update kernel completes its columns of U with it.
+__device__ __forceinline__ void gjp_panel_tail(const GjpBatch &g, int sys, int j, const double *M, const double *Lg, int *pps) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int ld = g.ld, lpad = g.lpad;
+    __syncthreads();  // the panel's global writes (pp, multipliers) are visible to the whole CTA
+    if (tid < kGjpNB) pps[tid] = g.pp[sys * kGjpNB + tid];
+    __syncthreads();
+    double *T = g.T + (size_t)sys * kGjpNB * kGjpNB;
+    for (int e = tid; e < kGjpNB * kGjpNB; e += nt) {
+        const int s = e >> 4, s1 = e & 15;
+        T[e] = (s1 < s && pps[s] >= 0 && pps[s1] >= 0) ? Lg[(size_t)s1 * lpad + pps[s]] : 0.;
+    }
+    double *U = g.U + (size_t)sys * kGjpNB * ld;
+    // one column pair per thread and trip, the 16 loads of a trip in flight together
+    const int c0 = (j + 1) * kGjpNB;
+    const double *rowp[kGjpNB];
+#pragma unroll
+    for (int s = 0; s < kGjpNB; ++s) rowp[s] = M + (size_t)(pps[s] >= 0 ? pps[s] : 0) * ld;
+    for (int c = c0 + 2 * tid; c < g.ncols; c += 2 * nt) {  // c0 and ld are even: 16-byte accesses, the pair stays inside the row
+        double2 v[kGjpNB];
+#pragma unroll
+        for (int s = 0; s < kGjpNB; ++s) v[s] = *reinterpret_cast<const double2 *>(rowp[s] + c);
+#pragma unroll
+        for (int s = 0; s < kGjpNB; ++s)
+            *reinterpret_cast<double2 *>(U + (size_t)s * ld + c) = pps[s] >= 0 ? v[s] : make_double2(0., 0.);
+    }
+}
+
+// Panel j (columns 16 j .. 16 j + 15 of A) of every system, rows in REGISTERS: thread t owns rows t + k blockDim.x,
+// k < RPT, and keeps their 16 panel entries in registers (the column loop is fully unrolled).  Per column two
+// barriers: the vote (warp arg-max by redux on the bit pattern of |a|, cross-warp through shared memory, re-reduced by
+// every warp) and the pivot row, which its owner publishes to shared memory.  n <= 576 RPT.
+template <int RPT>
+__global__ void __launch_bounds__(576, 1) k_gjp_panel(GjpBatch g, int j) {
+    __shared__ unsigned s_hi[32], s_lo[32];
+    __shared__ int s_row[32];
+    __shared__ double urow[2][kGjpNB];
+    __shared__ int pps[kGjpNB];
+    const int sys = gjp_system(g, blockIdx.x);
+    if (sys < 0) return;
+    const int n = g.n, ld = g.ld, lpad = g.lpad;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
+    double *Lg = g.L + (size_t)sys * kGjpNB * lpad;
+    int *used = g.used + (size_t)sys * n;
+    const int col0 = j * kGjpNB;
+    const int nb = min(kGjpNB, n - col0);
+    double a[RPT][kGjpNB];
+    unsigned um = 0;  // bit k: row tid + k nt has been a pivot row (or does not exist)
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int r = tid + k * nt;
+        if (r < n) {
+            const double2 *src = reinterpret_cast<const double2 *>(M + (size_t)r * ld + col0);  // 16-byte aligned: ld, col0 even
+#pragma unroll
+            for (int c = 0; c < kGjpNB; c += 2) {
+                const double2 v = src[c >> 1];
+                a[k][c] = c < nb ? v.x : 0.;
+                a[k][c + 1] = c + 1 < nb ? v.y : 0.;
+            }
+            if (j > 0) um |= (used[r] ? 1u : 0u) << k;
+            else used[r] = 0;  // a new system: the flags of the previous one are stale
+        } else {
+#pragma unroll
+            for (int c = 0; c < kGjpNB; ++c) a[k][c] = 0.;
+            um |= 1u << k;
+        }
+    }
+    if (j == 0 && tid == 0) g.fail[sys] = 0;
+#pragma unroll
+    for (int s = 0; s < kGjpNB; ++s) {
+        if (s >= nb) {  // past the last column: empty steps keep the update kernel uniform
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                if (tid + k * nt < n) Lg[(size_t)s * lpad + tid + k * nt] = 0.;
+            if (tid == 0) g.pp[sys * kGjpNB + s] = -1;
+            continue;
+        }
+        // arg-max of |a| over the rows not yet used; NaN entries never win (comparison false)
+        double best = -1.;
+        int bi = -1;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const double v = fabs(a[k][s]);
+            if (!((um >> k) & 1u) && v > best) { best = v; bi = tid + k * nt; }
+        }
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(best);
+        unsigned hi = bi >= 0 ? (unsigned)(bits >> 32) + 1u : 0u, lo = (unsigned)bits;
+        int row = bi;
+        gjp_warp_best(hi, lo, row);
+        if (lane == 0) { s_hi[warp] = hi; s_lo[warp] = lo; s_row[warp] = row; }
+        __syncthreads();
+        hi = lane < nwarp ? s_hi[lane] : 0u;
+        lo = lane < nwarp ? s_lo[lane] : 0u;
+        row = lane < nwarp ? s_row[lane] : -1;
+        gjp_warp_best(hi, lo, row);
+        const int p = row;  // identical in every thread
+        const int par = s & 1;
+        // the owner publishes the pivot row (its panel entries right of the pivot) and records the pivot
+#pragma unroll
+        for (int k = 0; k < RPT; ++k)
+            if (p >= 0 && tid + k * nt == p) {
+#pragma unroll
+                for (int c = s; c < kGjpNB; ++c) urow[par][c] = a[k][c];
+                um |= 1u << k;
+                used[p] = 1;
+                g.pp[sys * kGjpNB + s] = p;
+                g.rowof[(size_t)sys * n + col0 + s] = p;
+                g.piv[(size_t)sys * n + col0 + s] = a[k][s];
+            }
+        if (p < 0 && tid == 0) {  // no admissible pivot: the column is skipped, the system is reported as NaN
+            g.pp[sys * kGjpNB + s] = -1;
+            g.rowof[(size_t)sys * n + col0 + s] = -1;
+            g.piv[(size_t)sys * n + col0 + s] = 0.;
+            g.fail[sys] = 1;
+        }
+        __syncthreads();
+        if (p < 0) {
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                if (tid + k * nt < n) Lg[(size_t)s * lpad + tid + k * nt] = 0.;
+            continue;
+        }
+        const double rinv = 1. / urow[par][s];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = tid + k * nt;
+            if (r >= n) continue;
+            const double l = r == p ? 0. : -(a[k][s] * rinv);  // Gauss-Jordan: rows above the pivot are eliminated too
+            Lg[(size_t)s * lpad + r] = l;
+#pragma unroll
+            for (int c = s + 1; c < kGjpNB; ++c) a[k][c] = fma(l, urow[par][c], a[k][c]);
+        }
+    }
+    gjp_panel_tail(g, sys, j, M, Lg, pps);
+}
+
+// The same panel factorisation with the panel in shared memory (column-major, 16 * (n | 1) doubles): any n up to
+// ~14 000 rows, one barrier per column, about 4x the instructions of the register version.
+__global__ void __launch_bounds__(1024, 1) k_gjp_panel_smem(GjpBatch g, int j) {
+    extern __shared__ double P[];  // [16][npad] column-major panel
     __shared__ unsigned s_hi[2][32], s_lo[2][32];
     __shared__ int s_row[2][32];
+    __shared__ int pps[kGjpNB];
     const int sys = gjp_system(g, blockIdx.x);
     if (sys < 0) return;
     const int n = g.n, ld = g.ld, npad = n | 1, lpad = g.lpad;
@@ -91,12 +241,11 @@ __global__ void __launch_bounds__(1024) k_gjp_panel(GjpBatch g, int j) {
     __syncthreads();
     for (int s = 0; s < kGjpNB; ++s) {
         double *Ps = P + s * npad;
-        if (s >= nb) {  // past the last column: empty steps keep the update kernel uniform
+        if (s >= nb) {
             for (int r = tid; r < n; r += nt) Lg[(size_t)s * lpad + r] = 0.;
             if (tid == 0) g.pp[sys * kGjpNB + s] = -1;
             continue;
         }
-        // arg-max of |a| over the rows not yet used; NaN entries never win (comparison false)
         double best = -1.;
         int bi = -1;
         {
@@ -124,7 +273,7 @@ __global__ void __launch_bounds__(1024) k_gjp_panel(GjpBatch g, int j) {
             g.piv[(size_t)sys * n + col0 + s] = p >= 0 ? Ps[p] : 0.;
             if (p < 0) g.fail[sys] = 1;
         }
-        if (p < 0) {  // no admissible pivot: the column is skipped, the system is reported as NaN
+        if (p < 0) {
             for (int r = tid; r < n; r += nt) Lg[(size_t)s * lpad + r] = 0.;
             continue;
         }
@@ -146,85 +295,88 @@ __global__ void __launch_bounds__(1024) k_gjp_panel(GjpBatch g, int j) {
         }
         // the next step's barrier orders these writes (own rows only) before any other thread reads row p' of them
     }
+    gjp_panel_tail(g, sys, j, M, Lg, pps);
 }
 
-// Trailing update of panel j: columns c0 = 16 (j + 1) + CW * blockIdx.x ... of system blockIdx.y, all rows.
-template <int CW>
+// Trailing update of panel j on the tensor pipe:  M += L (n x 16) . U (16 x columns), U = the completed pivot rows.
+// One CTA = 128 rows x 32 columns (grid: column chunks right of the panel, row chunks, systems); one warp = 16 rows:
+// 2 x 4 tiles of 8 x 8, every operand loaded once, all global loads issued before the first barrier.  Warp 0 first
+// completes the CTA's 32 columns of the pivot-row snapshot, U[s] += sum_{s' < s} T[s][s'] U[s'] (sequential in s).
+constexpr int kGjpUpdCols = 32, kGjpUpdRows = 128;
 __global__ void __launch_bounds__(256) k_gjp_update(GjpBatch g, int j) {
-    __shared__ double Us[kGjpNB][CW + 4];
     __shared__ double Ts[kGjpNB][kGjpNB];
-    __shared__ int pps[kGjpNB];
-    const int sys = gjp_system(g, blockIdx.y);
+    __shared__ double Us[kGjpNB][kGjpUpdCols + 4];
+    const int sys = gjp_system(g, blockIdx.z);
     if (sys < 0) return;
     const int n = g.n, ld = g.ld, lpad = g.lpad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, t = lane & 3;
+    const int c0 = (j + 1) * kGjpNB + kGjpUpdCols * blockIdx.x;
+    const int r0 = kGjpUpdRows * blockIdx.y + 16 * warp;
     double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
     const double *Lg = g.L + (size_t)sys * kGjpNB * lpad;
-    const int c0 = (j + 1) * kGjpNB + CW * blockIdx.x;
-    if (c0 >= g.ncols) return;
-    if (tid < kGjpNB) pps[tid] = g.pp[sys * kGjpNB + tid];
-    __syncthreads();
-    // T[s][s'] = l_{s'}[p_s], s' < s: what pivot row s still owes to the panel's earlier pivots
-    {
-        const int s = tid >> 4, s1 = tid & 15;
-        Ts[s][s1] = (s1 < s && pps[s] >= 0 && pps[s1] >= 0) ? Lg[(size_t)s1 * lpad + pps[s]] : 0.;
+    const double *U = g.U + (size_t)sys * kGjpNB * ld;
+    Ts[tid >> 4][tid & 15] = g.T[(size_t)sys * kGjpNB * kGjpNB + tid];
+    for (int e = tid; e < kGjpNB * kGjpUpdCols; e += 256) {
+        const int s = e >> 5, c = e & 31;
+        Us[s][c] = c0 + c < g.ncols ? U[(size_t)s * ld + c0 + c] : 0.;
     }
-    for (int idx = tid; idx < kGjpNB * CW; idx += 256) {
-        const int s = idx / CW, c = idx - s * CW;
-        Us[s][c] = (pps[s] >= 0 && c0 + c < g.ncols) ? M[(size_t)pps[s] * ld + c0 + c] : 0.;
+    // this warp's operands: multipliers and C tiles (issued now, consumed after the barriers)
+    double af[2][4];
+    double2 cv[2][4];
+    bool rok[2], cok[4];
+#pragma unroll
+    for (int ct = 0; ct < 4; ++ct) cok[ct] = c0 + 8 * ct + 2 * t < g.ncols;  // ld is even: a pair never leaves the row
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = r0 + 8 * i + gq;
+        rok[i] = r < n;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) af[i][kk] = rok[i] ? Lg[(size_t)(4 * kk + t) * lpad + r] : 0.;
+        const double *crow = M + (size_t)(rok[i] ? r : 0) * ld + c0 + 2 * t;
+#pragma unroll
+        for (int ct = 0; ct < 4; ++ct)
+            cv[i][ct] = (rok[i] && cok[ct]) ? *reinterpret_cast<const double2 *>(crow + 8 * ct) : make_double2(0., 0.);
     }
     __syncthreads();
-    if (tid < CW) {  // u_s += sum_{s' < s} T[s][s'] u_{s'}, sequential in s
+    if (warp == 0) {
         double u[kGjpNB];
 #pragma unroll
-        for (int s = 0; s < kGjpNB; ++s) {
-            double a0 = Us[s][tid], a1 = 0.;
+        for (int s = 0; s < kGjpNB; ++s) u[s] = Us[s][lane];
 #pragma unroll
-            for (int s1 = 0; s1 + 1 < s; s1 += 2) {
-                a0 = fma(Ts[s][s1], u[s1], a0);
-                a1 = fma(Ts[s][s1 + 1], u[s1 + 1], a1);
+        for (int s = 1; s < kGjpNB; ++s) {
+            double a0 = u[s], a1 = 0.;
+#pragma unroll
+            for (int s1 = 0; s1 < kGjpNB; s1 += 2) {
+                if (s1 < s) a0 = fma(Ts[s][s1], u[s1], a0);
+                if (s1 + 1 < s) a1 = fma(Ts[s][s1 + 1], u[s1 + 1], a1);
             }
-            if (s & 1) a0 = fma(Ts[s][s - 1], u[s - 1], a0);
             u[s] = a0 + a1;
-            Us[s][tid] = u[s];
+            Us[s][lane] = u[s];
         }
     }
     __syncthreads();
-    // rank-16 update on the tensor pipe: rows 8 rt .. 8 rt + 7, column tiles of 8
-    const int gq = lane >> 2, t = lane & 3;
-    constexpr int NCT = CW / 8;
-    double bf[NCT][4];
+    double bf[4][4];
 #pragma unroll
-    for (int ct = 0; ct < NCT; ++ct)
+    for (int ct = 0; ct < 4; ++ct)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) bf[ct][kk] = Us[4 * kk + t][8 * ct + gq];
-    const int nrt = (n + 7) >> 3;
-    for (int rt = warp; rt < nrt; rt += 8) {
-        const int r = 8 * rt + gq;
-        const bool rok = r < n;
-        double a[4];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) a[kk] = rok ? Lg[(size_t)(4 * kk + t) * lpad + r] : 0.;
-        double *crow = M + (size_t)(rok ? r : 0) * ld + c0 + 2 * t;
-        double2 cv[NCT];
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int ct = 0; ct < NCT; ++ct) {
-            const bool cok = rok && c0 + 8 * ct + 2 * t < g.ncols;  // ld is even and > ncols: a pair never leaves the row
-            cv[ct] = cok ? *reinterpret_cast<const double2 *>(crow + 8 * ct) : make_double2(0., 0.);
-        }
+        for (int ct = 0; ct < 4; ++ct)
 #pragma unroll
-        for (int ct = 0; ct < NCT; ++ct)
+            for (int kk = 0; kk < 4; ++kk) dmma884(cv[i][ct].x, cv[i][ct].y, af[i][kk], bf[ct][kk]);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) dmma884(cv[ct].x, cv[ct].y, a[kk], bf[ct][kk]);
+    for (int i = 0; i < 2; ++i) {
+        double *crow = M + (size_t)(rok[i] ? r0 + 8 * i + gq : 0) * ld + c0 + 2 * t;
 #pragma unroll
-        for (int ct = 0; ct < NCT; ++ct) {
-            const bool cok = rok && c0 + 8 * ct + 2 * t < g.ncols;
-            if (cok) *reinterpret_cast<double2 *>(crow + 8 * ct) = cv[ct];
-        }
+        for (int ct = 0; ct < 4; ++ct)
+            if (rok[i] && cok[ct]) *reinterpret_cast<double2 *>(crow + 8 * ct) = cv[i][ct];
     }
 }
 
-// Carried columns -> solution: X[c][k] = M[rowof[c]][n + k] / piv[c].  out0 (optional): columns 0 .. nout0 - 1 of the
+// Carried columns -> solution: X[c][k] = M[rowof[c]][gjp_npc(n) + k] / piv[c].  out0 (optional): columns 0 .. nout0 - 1 of the
 // carried block, [n][ld0] row-major (pad columns zeroed); out1 (optional): carried column col1 as a vector [n].
 struct GjpFinish {
     double *out0;
@@ -247,7 +399,7 @@ __global__ void __launch_bounds__(256) k_gjp_finish(GjpBatch g, GjpFinish f) {
         const int r = g.rowof[(size_t)sys * n + c];
         const double pv = g.piv[(size_t)sys * n + c];
         const bool bad = fail || r < 0;
-        const double *src = M + (size_t)(bad ? 0 : r) * ld + n;
+        const double *src = M + (size_t)(bad ? 0 : r) * ld + gjp_npc(n);
         if (f.out0) {
             double *dst = f.out0 + (size_t)sys * f.out0_stride + f.out0_off + (size_t)c * f.ld0;
             for (int k = lane; k < f.ld0; k += 32) dst[k] = k < f.nout0 ? (bad ? nan : src[k] / pv) : 0.;
@@ -259,11 +411,11 @@ __global__ void __launch_bounds__(256) k_gjp_finish(GjpBatch g, GjpFinish f) {
 
 // ---------------------------------------------------------------------------------------------------------------- //
 // Block-Thomas engine: storage of one circuit's block-tridiagonal core (Nc block rows of S x S node blocks)
-//   block row r:  Mr [S][ldm]  = [ D_r | U_r (block (r, r+1)) | rhs_r | pad ],  ldm = 2 S + 2
+//   block row r:  Mr [S][ldm]  = [ D_r | pad to npc = gjp_npc(S) | U_r (block (r, r+1)) | rhs_r | pad ]
 //                 Lr [S][lds]  = sub-diagonal block (r, r-1) (pad column zero), lds = S + (S & 1) + ... even;
 //                                after block row r is eliminated its storage holds U'_r = D_r^-1 U_r
 // ---------------------------------------------------------------------------------------------------------------- //
-__host__ __device__ inline int btd_ldm(int S) { return 2 * S + 2; }
+__host__ __device__ inline int btd_ldm(int S) { return (gjp_npc(S) + S + 2) & ~1; }
 __host__ __device__ inline int btd_lds(int S) { return (S + 2) & ~1; }
 __host__ __device__ inline size_t btd_row_doubles(int S) { return (size_t)S * btd_ldm(S) + (size_t)S * btd_lds(S); }
 
@@ -309,7 +461,7 @@ __global__ void __launch_bounds__(256) k_btd_schur(SchurArgs a) {
             double acc = 0.;
             for (int k = lane; k < S; k += 32) acc = fma(ar[k], x[k], acc);
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-            if (lane == 0) Mr[(size_t)row * ldm + 2 * S] -= acc;
+            if (lane == 0) Mr[(size_t)row * ldm + gjp_npc(S) + S] -= acc;
         }
         return;
     }

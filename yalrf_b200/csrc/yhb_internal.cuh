@@ -159,6 +159,19 @@ struct Workspace {
     size_t j_stride;
     double *Inl;         // [B][W] optional output: nonlinear current spectrum of the last evaluation (or nullptr)
     double *Ic;          // [B][nb][S] optional output: collector-current samples of the last evaluation (:512)
+    // oscillator solve (yhb_solve_oscillator): circuits to leave alone, sensitivity output, d(linear admittance)/df
+    const int *skip;     // [B] or nullptr: circuit b is not solved (its oscillator is finished)
+    double *sens;        // [B][2][W] or nullptr: J^-1 dF/df and J^-1 dF/dA at the converged point (exact Jacobian)
+    double *dylin;       // [B][npair][K+1] or nullptr: f * d Im(ylin) / df  (capacitors +, inductors -)
+    int sens_src_n1, sens_src_n2;  // nodes of the probe current source (reference numbering): dF/dA = -dIs/dA
+    // buffers of the oscillator solve (carved for every batch; small next to the Newton state)
+    void *osc_state;     // [B] OscState
+    double *osc_Vacc;    // [B][W]
+    double *osc_Inl;     // [B][W]
+    double *osc_sens;    // [B][2][W]
+    double *osc_dylin;   // [B][npair][K+1]
+    int *osc_skip;       // [B]
+    int *osc_live;       // [1]
     double *pairwav;     // [B][npair_nl][2][S] pair conductance / capacitance waveforms (staged engine)
     double *xstep;       // [B][x_stride]  staged engine: Newton step vector + scratch of newton_pre / newton_post
     size_t x_stride;
@@ -167,6 +180,9 @@ struct Workspace {
     // (Wc for a dense core, S for the block rows of the block-Thomas engine), 0 = not used by this plan
     int gj_n, gj_lpad;
     double *gj_L;        // [B][16][gj_lpad] multipliers of the current panel
+    double *gj_U;        // [B][16][gj_ld]   snapshot of the pivot rows of the current panel
+    double *gj_T;        // [B][16][16]
+    int gj_ld;           // row stride of a system's working matrix
     double *gj_piv;      // [B][gj_n]
     int *gj_rowof;       // [B][gj_n]
     int *gj_used;        // [B][gj_n]
@@ -180,6 +196,13 @@ struct Workspace {
     int *dcinfo;         // [B][2]
     double *dcscratch;   // DC solver scratch
     size_t dc_stride;
+    // cold solves with the DC analysis overlapped (yhb_solve_cold): the HB kernel takes the circuits in order[] (most
+    // work first: sorted by the drive level key[]), waits for dc_ready[b] and builds its start vector from dcV itself
+    double *key;         // [B] sum of the AC source amplitudes (k_prepare)
+    int *order;          // [B] queue position -> circuit
+    int *dc_ready;       // [B] set by the DC kernel
+    int use_order;       // the fused kernel pops circuits through order[]
+    int dc_wait;         // the fused kernel waits for dc_ready[b] and initialises V from dcV (cold start)
 };
 
 void set_error(const std::string &msg);
