@@ -274,6 +274,13 @@ int yhb_solve_oscillator(const yhb_plan *plan, const yhb_params *p, const yhb_op
 int yhb_oscillator_host(const yhb_plan *plan, const yhb_params *host_params, const yhb_options *opt,
                         const yhb_osc_options *osc, const yhb_result *host_res, const yhb_osc_result *host_osc_res);
 
+/* ---- post-processing: convert_to_time (:125-135) and the quasi-periodic two-tone reconstruction the reference's
+ * notebooks do in a Python loop (tests/HB_TwoTones.ipynb cell 3).  Device pointers.
+ *   x[b][n][s] = Re Vf[b][n][0] + sum_{k >= 1} ( Re Vf[b][n][k] cos(2 pi f[b][k] t[s]) - Im Vf[b][n][k] sin(2 pi f[b][k] t[s]) )
+ * Vf[B][N][K1][2] phasors (hb.Vf), freqs[B][K1] bin frequencies (hb.freqs), t[nt] sample times, x[B][N][nt]. */
+int yhb_to_time(int32_t batch, int32_t N, int32_t K1, const double *Vf, const double *freqs, int32_t nt,
+                const double *t, double *x, void *stream);
+
 /* ---- stage entry points (parity tests / profiling); device pointers -------------------------------- */
 /* ifft (:706-713): vt[B][W] = IDFT applied per node */
 int yhb_stage_ifft(const yhb_plan *plan, int32_t batch, const double *V, double *vt, void *stream);

@@ -852,3 +852,36 @@ def test_block_pivoting_adversarial(yb, ac):
         assert conv
         assert hb.last.levels() == [l[1] for l in o.level_log], mode
         assert relmax(hb.V, o.V) < 1e-9, mode
+
+
+# ----------------------------------------------------------------------------- post-processing
+def test_convert_to_time_and_two_tone_reconstruction(yb, golden):
+    """convert_to_time (:125-135) and the two-tone reconstruction loop of tests/HB_TwoTones.ipynb cell 3 on the GPU
+    (yhb_to_time) against the reference's formulas evaluated in numpy."""
+    y = yb.YalRF('Diode Testbench')
+    h = circuits.hb_diode(y)
+    hb = mthb('HB1', h['freq'], h['K'])
+    assert hb.run(y)[0]
+    xf = hb.get_v('n2')
+    t, xt = hb.convert_to_time(xf)
+    S = 32 * hb.K
+    s = np.arange(S)[:, None]
+    k = np.arange(1, hb.K + 1)[None, :]
+    ref = xf[0].real + (xf[1:].real[None, :] * np.cos(2. * np.pi * k * s / (S / 2)) -
+                        xf[1:].imag[None, :] * np.sin(2. * np.pi * k * s / (S / 2))).sum(axis=1)
+    np.testing.assert_array_equal(t, 2 / hb.freq / S * np.linspace(0, S, S))
+    assert np.max(np.abs(xt - ref)) < 1e-12 * np.max(np.abs(ref))
+    # two tones: quasi-periodic waveform at arbitrary times
+    y2 = yb.YalRF('Diode Testbench')
+    h2 = circuits.hb_diode_two_tones(y2)
+    hb2 = mthb('HB1', h2['freq'], [3, 3])
+    conv, freqs, Vf, _, _ = hb2.run(y2)
+    assert conv
+    tt = np.arange(500) * (1. / (8. * np.max(freqs)))
+    x = hb2.to_time(['n1', 'n2'], tt)
+    for row, node in zip(x, ['n1', 'n2']):
+        v = hb2.get_v(node)
+        ref = v[0].real + sum(v[i].real * np.cos(2. * np.pi * freqs[i] * tt) - v[i].imag * np.sin(2. * np.pi * freqs[i] * tt)
+                              for i in range(1, len(freqs)))
+        assert np.max(np.abs(row - ref)) < 1e-12 * np.max(np.abs(ref))
+    assert hb2.to_time('n2', tt).shape == (500,)

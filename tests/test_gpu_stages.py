@@ -248,3 +248,33 @@ def test_stage_gjp_singular_reports_nan():
     xs = x.cpu().numpy()
     assert np.isnan(xs[0]).all()
     assert relmax(xs[1], np.linalg.solve(A[1], b[1])) < 1e-9
+
+
+def test_device_protocol_methods_golden(golden):
+    """The reference's per-sample device protocol on the host mirror's device objects -- BJT.get_hb_params,
+    Diode.get_mthb_params, CubicNonLinearity.get_mthb_params (SURVEY 8b "device protocol") -- evaluates on the GPU
+    through the Newton loop's own model code: a few of the 512 golden evaluations of the unmodified reference each."""
+    import yalrf_b200
+    g = golden('bjt_model')
+    y = yalrf_b200.Netlist('x')
+    q = y.add_bjt('Q', 'b', 'c', 'e')
+    q.options.update(dict(zip(g['opt_names'].tolist(), g['opt_vals'].tolist())))
+    for i in (0, 7, 100, 311):
+        vb, vc, ve = g['vin'][i]
+        ob, oc, oe = g['vold'][i]
+        out = np.array(q.get_hb_params(vb, vc, ve, 0., 0, ob, oc, oe))
+        ref = g['out'][i]
+        assert out.shape == (14,)
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert np.max(np.abs(out[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-300)) < 1e-12
+    gd = golden('diode_model')
+    d = y.add_diode('D', 'b', 'e')
+    d.options.update(dict(zip(gd['opt_names'].tolist(), gd['opt_vals'].tolist())))
+    for i in (0, 5, 200):
+        gdi, idi = d.get_mthb_params(float(gd['vd'][i]), float(gd['vdold'][i]))
+        ref = gd['out'][i]
+        assert abs(gdi - ref[0]) <= 1e-12 * abs(ref[0]) and abs(idi - ref[1]) <= 1e-12 * abs(ref[1])
+    c = y.add_cubicnl('N', 'b', 'e', 1e-3)
+    gc, ic = c.get_mthb_params(0.3, 0.2)
+    assert gc == 2 * 1e-3 * 0.3 * 0.3 and ic == 1e-3 * 0.3 * 0.3 * 0.3       # CubicNonLinearity.py:36-41

@@ -143,3 +143,29 @@ def test_binding_and_integration_stub_match_header_structs():
             assert [f[0] for f in cls._fields_] == want, (cname, cls)
         assert ctypes.sizeof(getattr(_lib, pyname)) == ctypes.sizeof(ns[pyname])
     assert _lib.Result().struct_size == ctypes.sizeof(_lib.Result) == 8 * 11
+
+
+def test_linear_mthb_stamps_match_oracle():
+    """add_mthb_stamps of the host mirror's linear devices (the reference's calc_Y protocol, :686-695) against the
+    oracle's calc_Y: identical dense Y for the Peltz oscillator (inductor, capacitor, gyrator), the DiffAmp and HB_Diode."""
+    import yalrf_b200
+    from oracle import hb_oracle as ho
+    for build, f in ((circuits.peltz, 80e3), (circuits.diffamp, None), (circuits.hb_diode, None)):
+        y = yalrf_b200.Netlist('x')
+        h = build(y)
+        y.add_idealharmonicfilter('F', 'nq', 'gnd', float(f or h['freq']))
+        yo = ho.FlatNetlist()
+        build(yo)
+        yo.add_idealharmonicfilter('F', 'nq', 'gnd', float(f or h['freq']))
+        o = ho.HBOracle('HB1', float(f or h['freq']), h['K'])
+        o.netlist = yo
+        o.lin_devs, o.nonlin_devs = yo.get_linear_devices(), yo.get_nonlinear_devices()
+        o.setup_grid()
+        Yo = o.calc_Y()
+        S, N = 2 * h['K'] + 1, y.get_num_nodes() - 1
+        Y = np.zeros((N * S, N * S))
+        for dev in y.get_linear_devices():
+            if hasattr(dev, 'add_mthb_stamps'):                       # :692
+                for k in range(h['K'] + 1):
+                    dev.add_mthb_stamps(Y, S, abs(o.freqs[k]), k)
+        assert np.array_equal(Y, Yo)

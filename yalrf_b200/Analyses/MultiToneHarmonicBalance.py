@@ -282,14 +282,25 @@ class MultiToneHarmonicBalance:
         return self.Vf[n]
 
     def convert_to_time(self, xf):
+        """:125-135 -- single-tone waveform of one node's phasors xf[K+1], 32 K samples over two periods; evaluated on
+        the GPU (yhb_to_time).  Returns (t, xt) like the reference (whose t axis is linspace(0, S, S) * 2 / f / S)."""
         S = 32 * self.K
         t = 2 / self.freq / S * np.linspace(0, S, S)
-        s = np.arange(S)[:, None]
-        k = np.arange(1, self.K + 1)[None, :]
-        xf = np.asarray(xf)
-        ang = 2. * np.pi * k * s / (S / 2)
-        xt = xf[0].real + (xf[1:].real[None, :] * np.cos(ang) - xf[1:].imag[None, :] * np.sin(ang)).sum(axis=1)
+        xf = np.asarray(xf, dtype=np.complex128).reshape(1, 1, -1)
+        # sample s sits at phase 2 pi k s / (S / 2): bin 'frequencies' k, 'times' s / (S / 2)
+        xt = E.to_time(xf, np.arange(self.K + 1, dtype=np.float64), np.arange(S) / (S / 2))[0, 0]
         return t, xt
+
+    def to_time(self, nodes, t, Vf=None, freqs=None):
+        """Quasi-periodic time-domain reconstruction (one or two tones) of node voltages at the times t, on the GPU:
+        the loop of tests/HB_TwoTones.ipynb cell 3.  nodes: a node name or a list of names; Vf / freqs default to the
+        last run's hb.Vf / hb.freqs.  Returns x[len(nodes)][len(t)] (or x[len(t)] for a single name)."""
+        Vf = self.Vf if Vf is None else Vf
+        freqs = self.freqs if freqs is None else freqs
+        single = isinstance(nodes, str)
+        idx = [self.get_node_idx(n) for n in ([nodes] if single else nodes)]
+        x = E.to_time(np.asarray(Vf)[idx][None], freqs, t)[0]
+        return x[0] if single else x
 
     def plot_v(self, node):
         """:35-110 -- needs matplotlib, which is an optional dependency here."""

@@ -287,3 +287,23 @@ class DeviceBatch:
         L.check(lib.yhb_solve(self.plan.handle, C.byref(self.params), C.byref(o), self.ws.data_ptr(), self.ws_bytes,
                               1 if have_v0 else 0, self.Vdc.data_ptr() if self.dc_done else None,
                               C.byref(self.result), st))
+
+
+def to_time(Vf, freqs, t):
+    """Time-domain waveforms of phasors on the GPU (yhb_to_time): Vf[B][N][K1] complex, freqs[B][K1] (or [K1]), t[nt]
+    -> x[B][N][nt].  The reference does this in Python loops (convert_to_time :125-135, HB_TwoTones.ipynb cell 3)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('yalrf_b200 needs a CUDA device: there is no CPU fallback')
+    Vf = np.ascontiguousarray(Vf, dtype=np.complex128)
+    B, N, K1 = Vf.shape
+    f = np.ascontiguousarray(np.broadcast_to(np.asarray(freqs, dtype=np.float64), (B, K1)))
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    L.check(L.lib().yhb_set_device(dev.index))
+    dV = torch.from_numpy(Vf.view(np.float64).reshape(B, N, K1, 2)).to(dev)
+    df, dt = torch.from_numpy(f).to(dev), torch.from_numpy(t).to(dev)
+    x = torch.empty((B, N, len(t)), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(L.lib().yhb_to_time(B, N, K1, dV.data_ptr(), df.data_ptr(), len(t), dt.data_ptr(), x.data_ptr(), st))
+    return x.cpu().numpy()

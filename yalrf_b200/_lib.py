@@ -90,7 +90,7 @@ PROF_KINDS = ['prepare', 'dc', 'init', 'eval', 'assemble', 'lu', 'finish', 'fuse
 EXPORTS = ['yhb_last_error', 'yhb_version', 'yhb_set_device', 'yhb_profile_enable', 'yhb_profile_reset',
            'yhb_profile_read', 'yhb_fp64_peak', 'yhb_plan_create', 'yhb_plan_destroy',
            'yhb_plan_dims', 'yhb_plan_core', 'yhb_plan_band', 'yhb_plan_engine', 'yhb_plan_block_sparse', 'yhb_plan_flops', 'yhb_plan_freqs', 'yhb_workspace_bytes', 'yhb_dc_solve', 'yhb_solve', 'yhb_solve_cold', 'yhb_newton',
-           'yhb_run_host', 'yhb_solve_oscillator', 'yhb_oscillator_host', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu', 'yhb_stage_gj', 'yhb_stage_gjp', 'yhb_debug_timing']
+           'yhb_run_host', 'yhb_solve_oscillator', 'yhb_oscillator_host', 'yhb_to_time', 'yhb_stage_ifft', 'yhb_stage_device_eval', 'yhb_stage_assemble', 'yhb_stage_lu', 'yhb_stage_gj', 'yhb_stage_gjp', 'yhb_debug_timing']
 
 
 def lib():
@@ -133,6 +133,8 @@ def lib():
                                        C.c_size_t, C.POINTER(Result), C.POINTER(OscResult), C.c_void_p]
     L.yhb_oscillator_host.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Options), C.POINTER(OscOptions),
                                       C.POINTER(Result), C.POINTER(OscResult)]
+    L.yhb_to_time.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                              C.c_void_p]
     L.yhb_stage_ifft.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.yhb_stage_device_eval.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]

@@ -2030,6 +2030,43 @@ extern "C" int yhb_stage_lu(int32_t batch, int32_t W, double *J, const double *F
     return 0;
 }
 
+// ---- post-processing: phasors -> time-domain waveforms (convert_to_time :125-135, tests/HB_TwoTones.ipynb cell 3) ----
+namespace yhb {
+__global__ void __launch_bounds__(256) k_to_time(int N, int K1, const double *Vf, const double *freqs, int nt,
+                                                 const double *t, double *x) {
+    extern __shared__ double sh[];  // phasors of this (circuit, node): re[K1], im[K1], then f[K1]
+    const int bn = blockIdx.y, b = bn / N;
+    double *re = sh, *im = sh + K1, *f = sh + 2 * K1;
+    for (int k = threadIdx.x; k < K1; k += blockDim.x) {
+        re[k] = Vf[2 * ((size_t)bn * K1 + k)];
+        im[k] = Vf[2 * ((size_t)bn * K1 + k) + 1];
+        f[k] = freqs[(size_t)b * K1 + k];
+    }
+    __syncthreads();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nt) return;
+    const double ts = t[s];
+    double acc = re[0];
+    for (int k = 1; k < K1; ++k) {  // the reference's loop, term by term in its order
+        double sn, cs;
+        sincos(kTwoPi * f[k] * ts, &sn, &cs);
+        acc = acc + re[k] * cs - im[k] * sn;
+    }
+    x[(size_t)bn * nt + s] = acc;
+}
+}  // namespace yhb
+
+extern "C" int yhb_to_time(int32_t batch, int32_t N, int32_t K1, const double *Vf, const double *freqs, int32_t nt,
+                           const double *t, double *x, void *stream) {
+    if (batch < 1 || N < 1 || K1 < 1 || nt < 1 || !Vf || !freqs || !t || !x) { set_error("bad argument"); return -1; }
+    const size_t smem = 3 * (size_t)K1 * sizeof(double);
+    if (smem > 200 * 1024) { set_error("yhb_to_time: too many bins"); return -1; }
+    if (smem > 48 * 1024) YHB_CUDA(cudaFuncSetAttribute(k_to_time, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_to_time<<<dim3((nt + 255) / 256, batch * N), 256, smem, (cudaStream_t)stream>>>(N, K1, Vf, freqs, nt, t, x);
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---- FP64 pipe peak (roofline denominator of the LU stage) -----------------------------------------
 namespace yhb {
 __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters) {
