@@ -1051,7 +1051,7 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.dcscratch = c.take<double>((size_t)B * ws.dc_stride);
     ws.key = c.take<double>(B);
     ws.order = c.take<int>(B);
-    ws.dc_ready = c.take<int>(B);
+    ws.dc_ready = c.take<int>((size_t)B + 4);  // + the two tickets of the persistent DC kernel's queue
     ws.use_order = 0;
     ws.dc_wait = 0;
     L.dd = c.take<DiodeDerived>((size_t)B * std::max(d.nd, 1));
@@ -1229,8 +1229,21 @@ int block_thomas_solve(const PlanDev &d, const Workspace &ws, const int *list, i
 }
 
 // calc_V0 (:697-704) = DC.run (DC.py:54-123) for the batch.  order / ready: see DcArgs (overlap with the HB kernel).
+size_t dc_warp_smem(const yhb_plan *pl) {
+    const PlanDev &d = pl->d;
+    const int M = d.N + pl->num_inductors, LD = (M + 1) | 1, nnl = d.nd + d.nb + d.nc;
+    return ((size_t)M * M + M + (size_t)kDcOut * std::max(nnl, 1) + (size_t)M * LD) * sizeof(double) +
+           (size_t)pl->dc_ent_ints * sizeof(int);
+}
+
+// queue != nullptr (one-warp engine only): persistent grid of queue_grid one-warp CTAs + ready list, see DcArgs.
+bool dc_one_warp(const yhb_plan *pl) {
+    const char *dc_env = getenv("YHB_DC_ENGINE");  // read per call: tests flip it within one process
+    return pl->dc_warp && !(dc_env && !strcmp(dc_env, "block"));
+}
+
 int dc_launch(const yhb_plan *pl, const yhb_params *p, const Layout &L, double *Vdc, int32_t *dc_info, const int *order,
-              int *ready, cudaStream_t st) {
+              int *ready, cudaStream_t st, int *queue = nullptr, int queue_grid = 0) {
     const PlanDev &d = pl->d;
     DcArgs a;
     a.lin_val = p->lin_val;
@@ -1252,20 +1265,19 @@ int dc_launch(const yhb_plan *pl, const yhb_params *p, const Layout &L, double *
     a.lane_tab = pl->dc_lane_dev;
     a.order = order;
     a.ready = ready;
+    a.queue = queue;
     a.use_smem = 0;
     // YHB_DC_ENGINE=block forces the general engine (A/B runs, parity tests of the one-warp engine against it)
-    const char *dc_env = getenv("YHB_DC_ENGINE");  // read per call: tests flip it within one process
-    const bool force_block = dc_env && !strcmp(dc_env, "block");
-    if (pl->dc_warp && !force_block) {
-        const int LD = (a.M + 1) | 1;
-        const size_t smw = ((size_t)a.M * a.M + a.M + (size_t)kDcOut * std::max(a.nnl, 1) + (size_t)a.M * LD) * sizeof(double) +
-                           (size_t)a.ent_ints * sizeof(int);
+    if (dc_one_warp(pl)) {
+        const size_t smw = dc_warp_smem(pl);
+        const int grid = queue ? std::min(p->batch, std::max(1, queue_grid)) : p->batch;
         ProfScope ps(PK_DC, st);
-        if (a.M <= 12) k_dc_warp<12><<<p->batch, 32, smw, st>>>(d, a, p->batch);
-        else k_dc_warp<24><<<p->batch, 32, smw, st>>>(d, a, p->batch);
+        if (a.M <= 12) k_dc_warp<12><<<grid, 32, smw, st>>>(d, a, p->batch);
+        else k_dc_warp<24><<<grid, 32, smw, st>>>(d, a, p->batch);
         YHB_CUDA(cudaGetLastError());
         return 0;
     }
+    if (queue) { set_error("internal: the DC queue needs the one-warp engine"); return -4; }
     size_t dsm = (a.M + 2) * sizeof(double);
     a.use_smem = (dsm + a.stride * sizeof(double)) <= 40 * 1024;  // small circuits: the whole DC analysis on chip
     if (a.use_smem) dsm += a.stride * sizeof(double);
@@ -1277,7 +1289,35 @@ int dc_launch(const yhb_plan *pl, const yhb_params *p, const Layout &L, double *
     return 0;
 }
 
-// DC analysis to run beside the fused HB kernel (yhb_solve_cold): outputs of the DC kernel
+// occupancy / attributes / launch of the fused kernel variant NT
+#define YHB_FUSED_CASES(X) X(0) X(1) YHB_FOR_NT(X)
+int fused_query(int NT, int fsmem, int *per_sm, cudaFuncAttributes *fa) {
+#define YHB_Q(t)                                                                                                  \
+    case t:                                                                                                       \
+        YHB_CUDA(cudaFuncSetAttribute(k_fused<t>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));            \
+        YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_fused<t>, fused_threads(t), fsmem));      \
+        YHB_CUDA(cudaFuncGetAttributes(fa, k_fused<t>));                                                           \
+        return 0;
+    switch (NT) {
+        YHB_FUSED_CASES(YHB_Q)
+        default: set_error("no fused kernel for this core size"); return -4;
+    }
+#undef YHB_Q
+}
+int fused_launch(int NT, int grid, int fsmem, cudaStream_t st, const PlanDev &d, const Workspace &ws, const EvalArgs &ea,
+                 int hot) {
+#define YHB_L(t) \
+    case t: k_fused<t><<<grid, fused_threads(t), fsmem, st>>>(d, ws, ea, hot); break;
+    switch (NT) {
+        YHB_FUSED_CASES(YHB_L)
+        default: set_error("no fused kernel for this core size"); return -4;
+    }
+#undef YHB_L
+    YHB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// DC analysis inside a cold solve (yhb_solve_cold): outputs of the DC kernel
 struct DcOverlap {
     double *Vdc;
     int32_t *info;
@@ -1292,59 +1332,97 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
     const PlanDev &d = pl->d;
     const int B = p->batch;
     Workspace &ws = L.ws;
-    if (dco) {
-        if (!L.fused || have_v0) { set_error("internal: DC overlap needs the fused engine and a cold start"); return -4; }
-        if (!pl->dc_stream) {
-            int lo = 0, hi = 0;
-            YHB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            YHB_CUDA(cudaStreamCreateWithPriority(&pl->dc_stream, cudaStreamNonBlocking, hi));
-            YHB_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
-            YHB_CUDA(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+    // dc_warps > 0: the DC kernel runs BESIDE the HB kernel (that many of its warps fit an SM next to all but one of the
+    // HB kernel's CTAs); dc_grid: its grid (one warp per circuit unless YHB_DC_WARPS asks for a persistent grid)
+    int fused_per_sm = 0, sms = 0, dc_warps = 0, dc_grid = p->batch;
+    if (L.fused) {
+        int dev = 0;
+        YHB_CUDA(cudaGetDevice(&dev));
+        YHB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cudaFuncAttributes fa;
+        if (int rc = fused_query(L.fc.NT, (int)L.fc.smem, &fused_per_sm, &fa)) return rc;
+        fused_per_sm = std::max(1, fused_per_sm);
+        // The DC analysis runs IN FRONT of the HB kernel by default.  YHB_DC_OVERLAP=1 runs it beside the HB kernel instead
+        // (side stream, ready list); measured on B200 (4096 DiffAmp circuits): 18.73 ms per sweep against 18.70 ms -- the
+        // one-warp DC chains stretch from 2.9 to 8.1 ms when they share the issue slots with HB CTAs, which meanwhile run
+        // two per SM instead of three.  Kept for experiments; the parity suite passes in both modes.
+        static const bool overlap = getenv("YHB_DC_OVERLAP") != nullptr;
+        if (dco && overlap && dc_one_warp(pl) && fused_per_sm >= 2) {
+            // Room for DC warps beside (fused_per_sm - 1) CTAs of the HB kernel on an SM.  The HB kernel's first launch is
+            // limited to that many CTAs per SM, so it can never occupy the whole device while it waits for operating points
+            // (an SM with fused_per_sm of them implies another with room to spare): DC warps can always become resident,
+            // whatever order the hardware places the two grids in.
+            int regs_sm = 0, smem_sm = 0;
+            YHB_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+            YHB_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+            cudaFuncAttributes da;
+            const int Mdc = d.N + pl->num_inductors;
+            if (Mdc <= 12) YHB_CUDA(cudaFuncGetAttributes(&da, k_dc_warp<12>));
+            else YHB_CUDA(cudaFuncGetAttributes(&da, k_dc_warp<24>));
+            const long regs_left = (long)regs_sm - (long)(fused_per_sm - 1) * fa.numRegs * fused_threads(L.fc.NT);
+            const long smem_left = (long)smem_sm - (long)(fused_per_sm - 1) * ((long)L.fc.smem + (long)fa.sharedSizeBytes + 1024);
+            const long by_regs = regs_left / std::max(1, da.numRegs * 32);
+            const long by_smem = smem_left / (long)(dc_warp_smem(pl) + da.sharedSizeBytes + 1024);
+            const char *e = getenv("YHB_DC_WARPS");  // A/B runs: a persistent grid of that many DC warps per SM
+            dc_warps = (int)std::max(0l, std::min(by_regs, by_smem));
+            if (e && dc_warps > 0) dc_grid = std::max(1, std::min(dc_warps, atoi(e))) * sms;
+            if (getenv("YHB_DEBUG"))
+                fprintf(stderr, "yhb: DC beside the HB kernel: %d warps per SM (registers allow %ld, shared memory %ld)\n", dc_warps,
+                        by_regs, by_smem);
         }
+    }
+    if (dco) {
+        if (!L.fused || have_v0) { set_error("internal: the fused cold solve needs the fused engine and a cold start"); return -4; }
         ws.use_order = 1;
-        ws.dc_wait = 1;
         ws.dc_valid = 1;
         if (dco->Vdc) ws.dcV = dco->Vdc;
-        YHB_CUDA(cudaMemsetAsync(ws.dc_ready, 0, sizeof(int) * (size_t)B, st));
+        if (dc_warps > 0) {
+            if (!pl->dc_stream) {
+                int lo = 0, hi = 0;
+                YHB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                YHB_CUDA(cudaStreamCreateWithPriority(&pl->dc_stream, cudaStreamNonBlocking, hi));
+                YHB_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+                YHB_CUDA(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+            }
+            ws.dc_wait = 2;  // persistent DC warps + ready list (DcArgs::queue)
+            YHB_CUDA(cudaMemsetAsync(ws.dc_ready, 0, sizeof(int) * ((size_t)B + 4), st));
+        }
     }
     if (int rc = launch_prepare(pl, p, L, st)) return rc;
+    if (dco && dc_warps == 0)  // no room beside the HB kernel (or the general DC engine): DC first, on the same stream
+        if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, nullptr, nullptr, st)) return rc;
     {
         ProfScope ps(PK_INIT, st);
         k_init<<<B, 128, 0, st>>>(d, ws, have_v0, alpha_fixed);
     }
     YHB_CUDA(cudaGetLastError());
-    if (dco) {  // fork: the DC kernel is launched FIRST, on the high-priority stream, in the HB kernel's work order
+    if (dc_warps > 0) {  // fork: the DC kernel goes first, on the high-priority stream, in the HB kernel's work order
         YHB_CUDA(cudaEventRecord(pl->ev_fork, st));
         YHB_CUDA(cudaStreamWaitEvent(pl->dc_stream, pl->ev_fork, 0));
-        if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, ws.order, ws.dc_ready, pl->dc_stream)) return rc;
-        YHB_CUDA(cudaEventRecord(pl->ev_join, pl->dc_stream));
+        if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, ws.order, ws.dc_ready, pl->dc_stream, ws.dc_ready + B, dc_grid))
+            return rc;
     }
     EvalArgs ea = eval_args(pl, p, opt, L);
     if (L.fused) {
-        const int fsmem = (int)L.fc.smem;
-        int dev = 0, sms = 0;
-        YHB_CUDA(cudaGetDevice(&dev));
-        YHB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         // persistent CTAs pulling circuits from a queue: grid = resident CTAs per SM x SMs
-#define YHB_LAUNCH_FUSED(t)                                                                                   \
-    case t: {                                                                                                 \
-        YHB_CUDA(cudaFuncSetAttribute(k_fused<t>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));        \
-        int per_sm = 0;                                                                                       \
-        YHB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<t>, fused_threads(t), fsmem)); \
-        const int grid = std::min(B, std::max(1, per_sm) * sms);                                              \
-        if (getenv("YHB_DEBUG"))                                                                              \
-            fprintf(stderr, "yhb: k_fused<%d> threads %d smem %d B, %d CTAs/SM, grid %d, block-sparse %d\n", t,   \
-                    fused_threads(t), fsmem, per_sm, grid, d.bs_ok);                                          \
-        ProfScope ps(PK_FUSED, st);                                                                           \
-        k_fused<t><<<grid, fused_threads(t), fsmem, st>>>(d, ws, ea, L.fc.hot);                                      \
-    } break;
-        switch (L.fc.NT) {
-            YHB_LAUNCH_FUSED(0) YHB_LAUNCH_FUSED(1) YHB_FOR_NT(YHB_LAUNCH_FUSED)
-            default: set_error("no fused kernel for this core size"); return -4;
+        const int full = fused_per_sm * sms;
+        const int grid = std::min(B, dc_warps > 0 ? (fused_per_sm - 1) * sms : full);
+        if (getenv("YHB_DEBUG"))
+            fprintf(stderr, "yhb: k_fused<%d> threads %d smem %d B, %d CTAs/SM, grid %d, block-sparse %d\n", L.fc.NT,
+                    fused_threads(L.fc.NT), (int)L.fc.smem, fused_per_sm, grid, d.bs_ok);
+        {
+            ProfScope ps(PK_FUSED, st);
+            if (int rc = fused_launch(L.fc.NT, grid, (int)L.fc.smem, st, d, ws, ea, L.fc.hot)) return rc;
         }
-#undef YHB_LAUNCH_FUSED
-        YHB_CUDA(cudaGetLastError());
-        if (dco) YHB_CUDA(cudaStreamWaitEvent(st, pl->ev_join, 0));  // join: Vdc / dc_info are complete for the caller
+        if (dc_warps > 0) {
+            // once the DC queue has drained its warps leave, and the last CTA per SM of the HB kernel moves in (second
+            // launch on the DC stream, same work queue); join: Vdc / dc_info are complete for the caller
+            const int more = std::min(std::max(B - grid, 0), full - grid);
+            if (more > 0)
+                if (int rc = fused_launch(L.fc.NT, more, (int)L.fc.smem, pl->dc_stream, d, ws, ea, L.fc.hot)) return rc;
+            YHB_CUDA(cudaEventRecord(pl->ev_join, pl->dc_stream));
+            YHB_CUDA(cudaStreamWaitEvent(st, pl->ev_join, 0));
+        }
         return launch_finish(pl, L, res, st);
     }
     const int smem = eval_smem_bytes(pl, L);
@@ -1465,8 +1543,7 @@ static int solve_cold(const yhb_plan *pl, const yhb_params *p, const yhb_options
     if (int rc = check_params(pl, p)) return rc;
     Layout L = carve(pl, p->batch, wsbuf);
     if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
-    static const bool no_overlap = getenv("YHB_NO_DC_OVERLAP") != nullptr;  // A/B runs
-    if (L.fused && !no_overlap) {
+    if (L.fused) {
         DcOverlap dco{Vdc ? Vdc : L.ws.dcV, dc_info ? dc_info : L.ws.dcinfo};
         return solve_common(pl, p, opt, wsbuf, ws_bytes, 0, nullptr, nullptr, res, stream, lock, &dco);
     }

@@ -44,6 +44,10 @@ struct DcArgs {
     // in which the HB kernel will ask for them) and publishes ready[b] = 1 once Vdc[b] is in memory
     const int *order;      // [B] or nullptr
     int *ready;            // [B] or nullptr
+    // one-warp engine beside the HB kernel (queue != nullptr): every warp pops slots from queue[0] until there are none
+    // left (any grid size), solves circuit order[slot] and appends it to the READY LIST: ready[queue[1]++] = b + 1
+    // (0 = not there yet).  The HB kernel pops the ready list in arrival order, so it never waits for a particular circuit.
+    int *queue;            // [2] pop ticket, push ticket (zeroed by the launcher) or nullptr
 };
 
 constexpr int kDcOut = 12;
@@ -740,13 +744,22 @@ struct DcWarp {
 
 template <int MMAX>
 #ifndef YHB_DC_WARP_MINBLOCKS
-#define YHB_DC_WARP_MINBLOCKS 1
+#define YHB_DC_WARP_MINBLOCKS 16  // 128 registers: six of these warps fit beside two CTAs of the fused HB kernel
 #endif
 __global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P, DcArgs a, int batch) {
     extern __shared__ double smw[];
-    if ((int)blockIdx.x >= batch) return;
-    const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
     const int M = a.M, N = P.N, lane = threadIdx.x;
+    if (!a.queue && (int)blockIdx.x >= batch) return;
+    int *tab = reinterpret_cast<int *>(smw + (size_t)M * M + M + (size_t)kDcOut * max(a.nnl, 1) + (size_t)M * ((M + 1) | 1));
+    for (int i = lane; i < a.ent_ints; i += 32) tab[i] = a.ent_tab[i];
+  for (;;) {
+    int slot = blockIdx.x;
+    if (a.queue) {
+        if (lane == 0) slot = atomicAdd(a.queue, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= batch) return;
+    }
+    const int b = a.order ? a.order[slot] : slot;
     DcWarp<MMAX> w;
     w.M = M;
     w.N = N;
@@ -757,8 +770,6 @@ __global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P
     w.z = w.A + M * M;
     w.dout = w.z + M;
     w.Aw = w.dout + (size_t)kDcOut * max(a.nnl, 1);
-    int *tab = reinterpret_cast<int *>(w.Aw + (size_t)M * w.LD);
-    for (int i = lane; i < a.ent_ints; i += 32) tab[i] = a.ent_tab[i];
     w.ent_ptr = tab;
     w.newton = 0;
     // role of this lane; hoisted constants with the operations of calc_dc
@@ -874,11 +885,20 @@ __global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P
         a.info[2 * b] = solved ? 1 : 0;
         a.info[2 * b + 1] = w.newton;
     }
+    if (a.queue) {  // append to the ready list
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(a.ready + atomicAdd(a.queue + 1, 1), b + 1);
+        __syncwarp();
+        continue;
+    }
     if (a.ready) {
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicExch(a.ready + b, 1);
     }
+    return;
+  }
 }
 
 }  // namespace yhb

@@ -200,9 +200,11 @@ struct Workspace {
     // work first: sorted by the drive level key[]), waits for dc_ready[b] and builds its start vector from dcV itself
     double *key;         // [B] sum of the AC source amplitudes (k_prepare)
     int *order;          // [B] queue position -> circuit
-    int *dc_ready;       // [B] set by the DC kernel
+    int *dc_ready;       // [B + 4] dc_wait = 1: flag per circuit; dc_wait = 2: ready list (circuit + 1 in arrival order), then
+                         // the persistent DC kernel's two queue tickets
     int use_order;       // the fused kernel pops circuits through order[]
-    int dc_wait;         // the fused kernel waits for dc_ready[b] and initialises V from dcV (cold start)
+    int dc_wait;         // the fused kernel waits for an operating point (1: of circuit order[ticket], 2: the ticket-th to
+                         // arrive) and initialises V from dcV (cold start)
 };
 
 void set_error(const std::string &msg);
