@@ -26,10 +26,11 @@ for nh in ([3, 3], [8, 8]):
     hb = MultiToneHarmonicBalance('HB1', h['freq'], nh)
     dt, _ = timeit(lambda: hb.run(y), reps=2); res['cfg3_%dx%d_single_s' % tuple(nh)] = dt
     res['cfg3_%dx%d_core' % tuple(nh)] = hb._plan.core()
-    B = 64
-    ac = np.linspace(0.1, 1.0, B)
-    dt, r = timeit(lambda: hb.run_sweep(y, [(h['i1'], 'ac', ac), (h['i2'], 'ac', ac)]), reps=1)
-    res['cfg3_%dx%d_sweep%d_solves_per_s' % (nh[0], nh[1], B)] = B / dt; res['cfg3_%dx%d_converged' % tuple(nh)] = int(r.converged.sum())
+    for B in (64, 512):   # batch over I1.ac = I2.ac in linspace(0.1, 1) (no batch size named)
+        ac = np.linspace(0.1, 1.0, B)
+        dt, r = timeit(lambda: hb.run_sweep(y, [(h['i1'], 'ac', ac), (h['i2'], 'ac', ac)]), reps=1)
+        res['cfg3_%dx%d_sweep%d_solves_per_s' % (nh[0], nh[1], B)] = B / dt
+        res['cfg3_%dx%d_sweep%d_converged' % (nh[0], nh[1], B)] = int(r.converged.sum())
 # config 2: Peltz oscillator
 y = yalrf_b200.Netlist('o'); h = circuits.peltz(y)
 hb = MultiToneHarmonicBalance('HB1')

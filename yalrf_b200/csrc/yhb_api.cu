@@ -1051,7 +1051,9 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.dcscratch = c.take<double>((size_t)B * ws.dc_stride);
     ws.key = c.take<double>(B);
     ws.order = c.take<int>(B);
-    ws.dc_ready = c.take<int>((size_t)B + 4);  // + the two tickets of the persistent DC kernel's queue
+    ws.dc_ready = c.take<int>((size_t)B + 8);  // + the counters of an overlapped cold solve
+    ws.dc_hash = c.take<unsigned long long>(B);
+    ws.dc_leader = c.take<int>(B);
     ws.use_order = 0;
     ws.dc_wait = 0;
     L.dd = c.take<DiodeDerived>((size_t)B * std::max(d.nd, 1));
@@ -1236,21 +1238,41 @@ size_t dc_warp_smem(const yhb_plan *pl) {
            (size_t)pl->dc_ent_ints * sizeof(int);
 }
 
-// queue != nullptr (one-warp engine only): persistent grid of queue_grid one-warp CTAs + ready list, see DcArgs.
 bool dc_one_warp(const yhb_plan *pl) {
     const char *dc_env = getenv("YHB_DC_ENGINE");  // read per call: tests flip it within one process
     return pl->dc_warp && !(dc_env && !strcmp(dc_env, "block"));
 }
 
-int dc_launch(const yhb_plan *pl, const yhb_params *p, const Layout &L, double *Vdc, int32_t *dc_info, const int *order,
-              int *ready, cudaStream_t st, int *queue = nullptr, int queue_grid = 0) {
-    const PlanDev &d = pl->d;
+// DcArgs with the fields both the grouping kernels and the DC kernels read
+DcArgs dc_inputs(const yhb_params *p) {
     DcArgs a;
+    memset(&a, 0, sizeof(a));
     a.lin_val = p->lin_val;
     a.src_val = p->src_val;
     a.diode_par = p->diode_par;
     a.bjt_par = p->bjt_par;
     a.cubic_par = p->cubic_par;
+    return a;
+}
+
+// Groups of circuits with bit-identical DC inputs -> ws.dc_leader (see k_dc_group).  force: also for a single circuit
+// (the HB kernel of an overlapped cold solve reads the leaders).  Returns the leader array, or nullptr when grouping is off.
+const int *dc_groups(const yhb_plan *pl, const yhb_params *p, const Layout &L, cudaStream_t st, bool force) {
+    static const bool no_groups = getenv("YHB_NO_DC_GROUPS") != nullptr;  // A/B runs
+    if (!force && (no_groups || p->batch < 2)) return nullptr;
+    const DcArgs a = dc_inputs(p);
+    ProfScope ps(PK_DC, st);
+    k_dc_hash<<<(p->batch + 3) / 4, 128, 0, st>>>(pl->d, a, p->batch, L.ws.dc_hash);
+    k_dc_group<<<(p->batch + 255) / 256, 256, 0, st>>>(pl->d, a, p->batch, L.ws.dc_hash, L.ws.dc_leader,
+                                                       force ? L.ws.dc_ready + p->batch + 3 : nullptr);
+    return L.ws.dc_leader;
+}
+
+// leader: groups from dc_groups() (only the leaders are solved, the others get copies) or nullptr
+int dc_launch(const yhb_plan *pl, const yhb_params *p, const Layout &L, double *Vdc, int32_t *dc_info, const int *order,
+              int *ready, cudaStream_t st, const int *leader) {
+    const PlanDev &d = pl->d;
+    DcArgs a = dc_inputs(p);
     a.lin_nodes = pl->lin_nodes_dev;
     a.nl_kind = pl->nl_kind_dev;
     a.nl_index = pl->nl_index_dev;
@@ -1265,25 +1287,27 @@ int dc_launch(const yhb_plan *pl, const yhb_params *p, const Layout &L, double *
     a.lane_tab = pl->dc_lane_dev;
     a.order = order;
     a.ready = ready;
-    a.queue = queue;
+    a.nready = ready ? L.ws.dc_ready + p->batch + 4 : nullptr;
+    a.leader = leader;
     a.use_smem = 0;
+    const bool groups = leader != nullptr;
     // YHB_DC_ENGINE=block forces the general engine (A/B runs, parity tests of the one-warp engine against it)
     if (dc_one_warp(pl)) {
         const size_t smw = dc_warp_smem(pl);
-        const int grid = queue ? std::min(p->batch, std::max(1, queue_grid)) : p->batch;
         ProfScope ps(PK_DC, st);
-        if (a.M <= 12) k_dc_warp<12><<<grid, 32, smw, st>>>(d, a, p->batch);
-        else k_dc_warp<24><<<grid, 32, smw, st>>>(d, a, p->batch);
+        if (a.M <= 12) k_dc_warp<12><<<p->batch, 32, smw, st>>>(d, a, p->batch);
+        else k_dc_warp<24><<<p->batch, 32, smw, st>>>(d, a, p->batch);
+        if (groups) k_dc_scatter<<<(p->batch + 255) / 256, 256, 0, st>>>(d.N, p->batch, a.leader, a.Vdc, a.info);
         YHB_CUDA(cudaGetLastError());
         return 0;
     }
-    if (queue) { set_error("internal: the DC queue needs the one-warp engine"); return -4; }
     size_t dsm = (a.M + 2) * sizeof(double);
     a.use_smem = (dsm + a.stride * sizeof(double)) <= 40 * 1024;  // small circuits: the whole DC analysis on chip
     if (a.use_smem) dsm += a.stride * sizeof(double);
     {
         ProfScope ps(PK_DC, st);
         k_dc<<<p->batch, kDcThreads, dsm, st>>>(d, a, p->batch);
+        if (groups) k_dc_scatter<<<(p->batch + 255) / 256, 256, 0, st>>>(d.N, p->batch, a.leader, a.Vdc, a.info);
     }
     YHB_CUDA(cudaGetLastError());
     return 0;
@@ -1333,8 +1357,8 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
     const int B = p->batch;
     Workspace &ws = L.ws;
     // dc_warps > 0: the DC kernel runs BESIDE the HB kernel (that many of its warps fit an SM next to all but one of the
-    // HB kernel's CTAs); dc_grid: its grid (one warp per circuit unless YHB_DC_WARPS asks for a persistent grid)
-    int fused_per_sm = 0, sms = 0, dc_warps = 0, dc_grid = p->batch;
+    // HB kernel's CTAs)
+    int fused_per_sm = 0, sms = 0, dc_warps = 0;
     if (L.fused) {
         int dev = 0;
         YHB_CUDA(cudaGetDevice(&dev));
@@ -1342,12 +1366,11 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
         cudaFuncAttributes fa;
         if (int rc = fused_query(L.fc.NT, (int)L.fc.smem, &fused_per_sm, &fa)) return rc;
         fused_per_sm = std::max(1, fused_per_sm);
-        // The DC analysis runs IN FRONT of the HB kernel by default.  YHB_DC_OVERLAP=1 runs it beside the HB kernel instead
-        // (side stream, ready list); measured on B200 (4096 DiffAmp circuits): 18.73 ms per sweep against 18.70 ms -- the
-        // one-warp DC chains stretch from 2.9 to 8.1 ms when they share the issue slots with HB CTAs, which meanwhile run
-        // two per SM instead of three.  Kept for experiments; the parity suite passes in both modes.
-        static const bool overlap = getenv("YHB_DC_OVERLAP") != nullptr;
-        if (dco && overlap && dc_one_warp(pl) && fused_per_sm >= 2) {
+        // Cold solves: circuits with identical DC inputs share one DC analysis (an amplitude sweep repeats every bias point),
+        // and the DC kernel -- as long as its slowest circuit, one warp per distinct problem -- runs BESIDE the HB kernel
+        // (side stream, a ready flag per distinct problem).  YHB_NO_DC_OVERLAP=1: DC first, on the same stream (A/B runs).
+        static const bool no_overlap = getenv("YHB_NO_DC_OVERLAP") != nullptr;
+        if (dco && !no_overlap && dc_one_warp(pl) && fused_per_sm >= 2) {
             // Room for DC warps beside (fused_per_sm - 1) CTAs of the HB kernel on an SM.  The HB kernel's first launch is
             // limited to that many CTAs per SM, so it can never occupy the whole device while it waits for operating points
             // (an SM with fused_per_sm of them implies another with room to spare): DC warps can always become resident,
@@ -1363,14 +1386,13 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
             const long smem_left = (long)smem_sm - (long)(fused_per_sm - 1) * ((long)L.fc.smem + (long)fa.sharedSizeBytes + 1024);
             const long by_regs = regs_left / std::max(1, da.numRegs * 32);
             const long by_smem = smem_left / (long)(dc_warp_smem(pl) + da.sharedSizeBytes + 1024);
-            const char *e = getenv("YHB_DC_WARPS");  // A/B runs: a persistent grid of that many DC warps per SM
             dc_warps = (int)std::max(0l, std::min(by_regs, by_smem));
-            if (e && dc_warps > 0) dc_grid = std::max(1, std::min(dc_warps, atoi(e))) * sms;
             if (getenv("YHB_DEBUG"))
-                fprintf(stderr, "yhb: DC beside the HB kernel: %d warps per SM (registers allow %ld, shared memory %ld)\n", dc_warps,
-                        by_regs, by_smem);
+                fprintf(stderr, "yhb: DC beside the HB kernel: room for %d warps per SM (registers allow %ld, shared memory %ld)\n",
+                        dc_warps, by_regs, by_smem);
         }
     }
+    const int *leader = nullptr;
     if (dco) {
         if (!L.fused || have_v0) { set_error("internal: the fused cold solve needs the fused engine and a cold start"); return -4; }
         ws.use_order = 1;
@@ -1384,23 +1406,23 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
                 YHB_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
                 YHB_CUDA(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
             }
-            ws.dc_wait = 2;  // persistent DC warps + ready list (DcArgs::queue)
-            YHB_CUDA(cudaMemsetAsync(ws.dc_ready, 0, sizeof(int) * ((size_t)B + 4), st));
+            ws.dc_wait = 1;
+            YHB_CUDA(cudaMemsetAsync(ws.dc_ready, 0, sizeof(int) * ((size_t)B + 8), st));
         }
+        leader = dc_groups(pl, p, L, st, dc_warps > 0);  // before the fork: the HB kernel reads the leaders too
     }
     if (int rc = launch_prepare(pl, p, L, st)) return rc;
     if (dco && dc_warps == 0)  // no room beside the HB kernel (or the general DC engine): DC first, on the same stream
-        if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, nullptr, nullptr, st)) return rc;
+        if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, nullptr, nullptr, st, leader)) return rc;
     {
         ProfScope ps(PK_INIT, st);
         k_init<<<B, 128, 0, st>>>(d, ws, have_v0, alpha_fixed);
     }
     YHB_CUDA(cudaGetLastError());
-    if (dc_warps > 0) {  // fork: the DC kernel goes first, on the high-priority stream, in the HB kernel's work order
+    if (dc_warps > 0) {  // fork: the DC kernel on the high-priority stream, in the HB kernel's work order
         YHB_CUDA(cudaEventRecord(pl->ev_fork, st));
         YHB_CUDA(cudaStreamWaitEvent(pl->dc_stream, pl->ev_fork, 0));
-        if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, ws.order, ws.dc_ready, pl->dc_stream, ws.dc_ready + B, dc_grid))
-            return rc;
+        if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, ws.order, ws.dc_ready, pl->dc_stream, leader)) return rc;
     }
     EvalArgs ea = eval_args(pl, p, opt, L);
     if (L.fused) {
@@ -1415,8 +1437,8 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
             if (int rc = fused_launch(L.fc.NT, grid, (int)L.fc.smem, st, d, ws, ea, L.fc.hot)) return rc;
         }
         if (dc_warps > 0) {
-            // once the DC queue has drained its warps leave, and the last CTA per SM of the HB kernel moves in (second
-            // launch on the DC stream, same work queue); join: Vdc / dc_info are complete for the caller
+            // when the DC kernel has finished, the last CTA per SM of the HB kernel moves in (second launch, on the DC
+            // stream, same work queue); join: Vdc / dc_info are complete for the caller
             const int more = std::min(std::max(B - grid, 0), full - grid);
             if (more > 0)
                 if (int rc = fused_launch(L.fc.NT, more, (int)L.fc.smem, pl->dc_stream, d, ws, ea, L.fc.hot)) return rc;
@@ -1512,7 +1534,8 @@ extern "C" int yhb_dc_solve(const yhb_plan *pl, const yhb_params *p, void *wsbuf
     if (int rc = check_params(pl, p)) return rc;
     Layout L = carve(pl, p->batch, wsbuf);
     if (!wsbuf || ws_bytes < L.bytes) { set_error("workspace too small"); return -1; }
-    return dc_launch(pl, p, L, Vdc, dc_info, nullptr, nullptr, (cudaStream_t)stream);
+    return dc_launch(pl, p, L, Vdc, dc_info, nullptr, nullptr, (cudaStream_t)stream,
+                     dc_groups(pl, p, L, (cudaStream_t)stream, false));
 }
 
 // lock = false: the caller (yhb_run_host) already holds pl->mu
@@ -1547,7 +1570,9 @@ static int solve_cold(const yhb_plan *pl, const yhb_params *p, const yhb_options
         DcOverlap dco{Vdc ? Vdc : L.ws.dcV, dc_info ? dc_info : L.ws.dcinfo};
         return solve_common(pl, p, opt, wsbuf, ws_bytes, 0, nullptr, nullptr, res, stream, lock, &dco);
     }
-    if (int rc = dc_launch(pl, p, L, Vdc, dc_info, nullptr, nullptr, (cudaStream_t)stream)) return rc;
+    if (int rc = dc_launch(pl, p, L, Vdc, dc_info, nullptr, nullptr, (cudaStream_t)stream,
+                           dc_groups(pl, p, L, (cudaStream_t)stream, false)))
+        return rc;
     return solve_common(pl, p, opt, wsbuf, ws_bytes, 0, Vdc ? Vdc : L.ws.dcV, nullptr, res, stream, lock);
 }
 

@@ -40,14 +40,14 @@ struct DcArgs {
                            // [items] contributions in stamping order: ((t * kDcOut + slot) << 1) | negate
     int ent_ints;
     const int *lane_tab;   // [32][kDcLaneInts] role of every lane in the device evaluation
-    // DC analysis overlapped with the harmonic-balance kernel (yhb_solve_cold): CTA i takes circuit order[i] (the order
-    // in which the HB kernel will ask for them) and publishes ready[b] = 1 once Vdc[b] is in memory
+    // DC analysis beside the harmonic-balance kernel (yhb_solve_cold, YHB_DC_OVERLAP): CTA i takes circuit order[i] (the
+    // order in which the HB kernel will ask for them) and publishes ready[b] = 1 once Vdc[b] is in memory
     const int *order;      // [B] or nullptr
     int *ready;            // [B] or nullptr
-    // one-warp engine beside the HB kernel (queue != nullptr): every warp pops slots from queue[0] until there are none
-    // left (any grid size), solves circuit order[slot] and appends it to the READY LIST: ready[queue[1]++] = b + 1
-    // (0 = not there yet).  The HB kernel pops the ready list in arrival order, so it never waits for a particular circuit.
-    int *queue;            // [2] pop ticket, push ticket (zeroed by the launcher) or nullptr
+    int *nready;           // counter of solved circuits (with ready) or nullptr
+    // circuits with bit-identical DC inputs (an amplitude sweep repeats every bias point): leader[b] = first circuit of
+    // b's group (k_dc_group); only leaders are solved, k_dc_scatter copies their results to the others
+    const int *leader;     // [B] or nullptr
 };
 
 constexpr int kDcOut = 12;
@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(kDcThreads) k_dc(PlanDev P, DcArgs a, int batc
     __shared__ int s_flag;
     if ((int)blockIdx.x >= batch) return;
     const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
+    if (a.leader && a.leader[b] != b) return;
     const int M = a.M, N = P.N, tid = threadIdx.x, nt = blockDim.x;
     DcCtx c;
     c.P = &P;
@@ -749,17 +750,11 @@ template <int MMAX>
 __global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P, DcArgs a, int batch) {
     extern __shared__ double smw[];
     const int M = a.M, N = P.N, lane = threadIdx.x;
-    if (!a.queue && (int)blockIdx.x >= batch) return;
+    if ((int)blockIdx.x >= batch) return;
+    const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
+    if (a.leader && a.leader[b] != b) return;
     int *tab = reinterpret_cast<int *>(smw + (size_t)M * M + M + (size_t)kDcOut * max(a.nnl, 1) + (size_t)M * ((M + 1) | 1));
     for (int i = lane; i < a.ent_ints; i += 32) tab[i] = a.ent_tab[i];
-  for (;;) {
-    int slot = blockIdx.x;
-    if (a.queue) {
-        if (lane == 0) slot = atomicAdd(a.queue, 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= batch) return;
-    }
-    const int b = a.order ? a.order[slot] : slot;
     DcWarp<MMAX> w;
     w.M = M;
     w.N = N;
@@ -885,20 +880,81 @@ __global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P
         a.info[2 * b] = solved ? 1 : 0;
         a.info[2 * b + 1] = w.newton;
     }
-    if (a.queue) {  // append to the ready list
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicExch(a.ready + atomicAdd(a.queue + 1, 1), b + 1);
-        __syncwarp();
-        continue;
-    }
     if (a.ready) {
         __threadfence();
         __syncwarp();
-        if (lane == 0) atomicExch(a.ready + b, 1);
+        if (lane == 0) {
+            atomicExch(a.ready + b, 1);
+            if (a.nready) atomicAdd(a.nready, 1);
+        }
     }
-    return;
-  }
+}
+
+// ---- circuits with identical DC inputs ------------------------------------------------------------------------------
+// The DC analysis reads the linear element values, the DC source values and the device parameters -- not the tones and
+// not the AC amplitudes / phases -- so the points of an amplitude or frequency sweep that share a bias point are ONE DC
+// problem.  word i of circuit b's DC inputs (a superset of what the DC kernels read), 0 <= i < dc_words():
+__device__ __forceinline__ int dc_words(const PlanDev &P) {
+    return P.nlin + P.nsrc + P.nd * YHB_DIODE_NPAR + P.nb * YHB_BJT_NPAR + P.nc;
+}
+__device__ __forceinline__ unsigned long long dc_word(const PlanDev &P, const DcArgs &a, int b, int i) {
+    double v;
+    if (i < P.nlin) v = a.lin_val[((size_t)b * P.nlin + i) * 2];
+    else if ((i -= P.nlin) < P.nsrc) v = a.src_val[((size_t)b * P.nsrc + i) * 3];
+    else if ((i -= P.nsrc) < P.nd * YHB_DIODE_NPAR) v = a.diode_par[(size_t)b * P.nd * YHB_DIODE_NPAR + i];
+    else if ((i -= P.nd * YHB_DIODE_NPAR) < P.nb * YHB_BJT_NPAR) v = a.bjt_par[(size_t)b * P.nb * YHB_BJT_NPAR + i];
+    else v = a.cubic_par[(size_t)b * P.nc + (i - P.nb * YHB_BJT_NPAR)];
+    return (unsigned long long)__double_as_longlong(v);
+}
+
+// one warp per circuit: order-independent 64-bit hash of the DC inputs (sum of mixed (word, position) pairs)
+__global__ void __launch_bounds__(128) k_dc_hash(PlanDev P, DcArgs a, int batch, unsigned long long *hash) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= batch) return;
+    const int nw = dc_words(P);
+    unsigned long long h = 0;
+    for (int i = lane; i < nw; i += 32) {
+        unsigned long long x = dc_word(P, a, b, i) + 0x9e3779b97f4a7c15ull * (unsigned long long)(i + 1);
+        x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+        x ^= x >> 27; x *= 0x94d049bb133111ebull;
+        x ^= x >> 31;
+        h += x;
+    }
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if (lane == 0) hash[b] = h;
+}
+
+// leader[b] = the first circuit of b's chunk (kDcGroupChunk circuits) whose DC inputs equal b's bit for bit
+constexpr int kDcGroupChunk = 8192;
+__global__ void __launch_bounds__(256) k_dc_group(PlanDev P, DcArgs a, int batch, const unsigned long long *hash, int *leader,
+                                                  int *nlead) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const int c0 = b / kDcGroupChunk * kDcGroupChunk;
+    const unsigned long long hb = hash[b];
+    const int nw = dc_words(P);
+    int lead = b;
+    for (int j = c0; j < b; ++j) {
+        if (hash[j] != hb) continue;
+        bool same = true;
+        for (int i = 0; i < nw && same; ++i) same = dc_word(P, a, j, i) == dc_word(P, a, b, i);
+        if (same) { lead = j; break; }
+    }
+    leader[b] = lead;
+    if (nlead && lead == b) atomicAdd(nlead, 1);
+}
+
+// results of the leaders to the other circuits of their groups
+__global__ void __launch_bounds__(256) k_dc_scatter(int N, int batch, const int *leader, double *Vdc, int *info) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const int l = leader[b];
+    if (l == b) return;
+    for (int n = 0; n < N; ++n) Vdc[(size_t)b * N + n] = Vdc[(size_t)l * N + n];
+    if (info) {
+        info[2 * b] = info[2 * l];
+        info[2 * b + 1] = info[2 * l + 1];
+    }
 }
 
 }  // namespace yhb

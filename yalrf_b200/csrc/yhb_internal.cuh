@@ -200,11 +200,13 @@ struct Workspace {
     // work first: sorted by the drive level key[]), waits for dc_ready[b] and builds its start vector from dcV itself
     double *key;         // [B] sum of the AC source amplitudes (k_prepare)
     int *order;          // [B] queue position -> circuit
-    int *dc_ready;       // [B + 4] dc_wait = 1: flag per circuit; dc_wait = 2: ready list (circuit + 1 in arrival order), then
-                         // the persistent DC kernel's two queue tickets
+    int *dc_ready;       // [B + 8] dc_ready[l] = 1: the DC point of circuit l (a group leader) is in dcV; then the counters of
+                         // an overlapped cold solve (see the ticket logic of k_fused)
+    unsigned long long *dc_hash;  // [B] hash of every circuit's DC inputs (k_dc_hash)
+    int *dc_leader;      // [B] first circuit with the same DC inputs (k_dc_group)
     int use_order;       // the fused kernel pops circuits through order[]
-    int dc_wait;         // the fused kernel waits for an operating point (1: of circuit order[ticket], 2: the ticket-th to
-                         // arrive) and initialises V from dcV (cold start)
+    int dc_wait;         // cold start beside the DC kernel: the fused kernel takes the circuits whose operating point (their
+                         // group leader's) has arrived, defers the others to list[0], and initialises V from dcV itself
 };
 
 void set_error(const std::string &msg);
