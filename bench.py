@@ -413,7 +413,16 @@ def run_gpu(args):
         total_ms = sum(m for _, m in prof.values())
         fl_ref, fl_core, fl_exec = plan.flops()
         kname = {'fused': 'k_fused', 'lu': 'k_solve_core', 'eval': 'k_eval', 'dc': 'k_dc_warp'}.get(kind, kind)
-        roof = {'kernel': kname, 'share_of_device_time': ms_l / total_ms if total_ms else None,
+        # the DC kernel runs BESIDE the HB kernel (side stream), so the kernels' own durations add up to more than the step:
+        # share_of_step = this kernel's duration / step duration (CUDA events); share_serialised = its share of the sum of all
+        # kernel durations, with the DC kernel at its stand-alone duration -- the figure an ncu launch list (serialised
+        # launches, profiles/r02_bench_launch_list_summary.txt) shows
+        dc_alone = ncu_summary('k_dc_warp')
+        dc_alone_ms = (dc_alone or {}).get('gpu_time_us')
+        ser_total = sum(m for k, (_, m) in prof.items() if k != 'dc') + (
+            dc_alone_ms * 1e-3 * prof['dc'][0] / 2 if dc_alone_ms and 'dc' in prof else prof.get('dc', (0, 0.))[1])
+        roof = {'kernel': kname, 'share_of_step': ms_l / ms if ms else None,
+                'share_serialised': ms_l / ser_total if ser_total else None,
                 'launches': n_l, 'avg_launch_ms': ms_l / max(n_l, 1), 'traffic': None}
         if kind in ('lu', 'fused'):
             per_s = lus * args.steps / (ms_l * 1e-3) / 1e12

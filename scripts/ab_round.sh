@@ -7,7 +7,7 @@ for v in $LIBS; do
   YHB_LIB=yalrf_b200/libyhb_$v.so python scripts/ab_value.py >> gpurun_out/${TAG}_ab.log 2>&1
 done
 for e in $ENVS; do
-  env $e python scripts/ab_value.py >> gpurun_out/${TAG}_ab.log 2>&1
+  env ${e//,/ } python scripts/ab_value.py >> gpurun_out/${TAG}_ab.log 2>&1
 done
 [ -f yalrf_b200/libyhb_timing.so ] && YHB_LIB=yalrf_b200/libyhb_timing.so python scripts/fused_timing.py > gpurun_out/${TAG}_timing.log 2>&1
 grep -v "^yhb:" gpurun_out/${TAG}_ab.log | cut -c1-420

@@ -47,20 +47,25 @@ if os.path.exists(src):
     print(open(out('bench_launch_list_summary.txt')).read())
 
 
-def raw_metrics(rep):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    if len(rows) < 3:
-        return {}
-    hdr, vals = rows[0], rows[2]
-    return dict(zip(hdr, vals))
-
-
 def num(x):
     try:
         return float(str(x).replace(',', ''))
     except Exception:
         return None
+
+
+def raw_metrics(rep):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) < 3:
+        return {}
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    scale = {'byte': 1., 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1., 'ms': 1e3, 's': 1e6}   # -> bytes, us
+    out = {}
+    for h, u, v in zip(hdr, units, vals):
+        x = num(v)
+        out[h] = x * scale[u] if (x is not None and u in scale) else v
+    return out
 
 
 summary = {}
@@ -86,7 +91,7 @@ for rep, name, what, key in [('fused_%s' % tag, 'bench_fused_full.txt', 'k_fused
         'dram_throughput_pct': num(m.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')),
         'stall_barrier_per_issue': num(m.get('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio')),
         'note': 'dram bytes: dram__bytes_read.sum + dram__bytes_write.sum of the captured launch (units as ncu reports them are '
-                'normalised to bytes by --page raw)',
+                'converted to bytes; gpu_time_us = gpu__time_duration.sum of the captured launch in microseconds',
     }
     print(open(out(name)).read())
 if summary:

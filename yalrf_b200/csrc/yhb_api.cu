@@ -1091,7 +1091,8 @@ int launch_prepare(const yhb_plan *pl, const yhb_params *p, const Layout &L, cud
     a.key = L.ws.use_order ? L.ws.key : nullptr;
     ProfScope ps(PK_PREPARE, st);
     k_prepare<<<p->batch, 128, 0, st>>>(pl->d, a, p->batch);
-    if (L.ws.use_order) k_order<<<(p->batch + 255) / 256, 256, 0, st>>>(L.ws.key, L.ws.order, p->batch);
+    if (L.ws.use_order)
+        k_order<<<(int)(((size_t)p->batch * kOrderLanes + 255) / 256), 256, 0, st>>>(L.ws.key, L.ws.order, p->batch);
     YHB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1263,7 +1264,7 @@ const int *dc_groups(const yhb_plan *pl, const yhb_params *p, const Layout &L, c
     const DcArgs a = dc_inputs(p);
     ProfScope ps(PK_DC, st);
     k_dc_hash<<<(p->batch + 3) / 4, 128, 0, st>>>(pl->d, a, p->batch, L.ws.dc_hash);
-    k_dc_group<<<(p->batch + 255) / 256, 256, 0, st>>>(pl->d, a, p->batch, L.ws.dc_hash, L.ws.dc_leader,
+    k_dc_group<<<(int)(((size_t)p->batch * kDcGroupLanes + 255) / 256), 256, 0, st>>>(pl->d, a, p->batch, L.ws.dc_hash, L.ws.dc_leader,
                                                        force ? L.ws.dc_ready + p->batch + 3 : nullptr);
     return L.ws.dc_leader;
 }
@@ -1288,6 +1289,7 @@ int dc_launch(const yhb_plan *pl, const yhb_params *p, const Layout &L, double *
     a.order = order;
     a.ready = ready;
     a.nready = ready ? L.ws.dc_ready + p->batch + 4 : nullptr;
+    a.nstarted = ready ? L.ws.dc_ready + p->batch + 5 : nullptr;
     a.leader = leader;
     a.use_smem = 0;
     const bool groups = leader != nullptr;
@@ -1356,9 +1358,9 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
     const PlanDev &d = pl->d;
     const int B = p->batch;
     Workspace &ws = L.ws;
-    // dc_warps > 0: the DC kernel runs BESIDE the HB kernel (that many of its warps fit an SM next to all but one of the
-    // HB kernel's CTAs)
-    int fused_per_sm = 0, sms = 0, dc_warps = 0;
+    // overlap: the DC kernel runs BESIDE the HB kernel
+    int fused_per_sm = 0, sms = 0;
+    bool overlap = false;
     if (L.fused) {
         int dev = 0;
         YHB_CUDA(cudaGetDevice(&dev));
@@ -1367,30 +1369,12 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
         if (int rc = fused_query(L.fc.NT, (int)L.fc.smem, &fused_per_sm, &fa)) return rc;
         fused_per_sm = std::max(1, fused_per_sm);
         // Cold solves: circuits with identical DC inputs share one DC analysis (an amplitude sweep repeats every bias point),
-        // and the DC kernel -- as long as its slowest circuit, one warp per distinct problem -- runs BESIDE the HB kernel
-        // (side stream, a ready flag per distinct problem).  YHB_NO_DC_OVERLAP=1: DC first, on the same stream (A/B runs).
+        // and the DC kernel -- as long as its slowest circuit, one warp per distinct problem -- runs BESIDE the HB kernel:
+        // side stream, a ready flag per distinct problem, and a gate kernel in front of the HB kernel that opens when every
+        // DC CTA has begun (resident or done), so that the waiting HB CTAs can never keep DC work off the device.
+        // YHB_NO_DC_OVERLAP=1: DC first, on the same stream (A/B runs).
         static const bool no_overlap = getenv("YHB_NO_DC_OVERLAP") != nullptr;
-        if (dco && !no_overlap && dc_one_warp(pl) && fused_per_sm >= 2) {
-            // Room for DC warps beside (fused_per_sm - 1) CTAs of the HB kernel on an SM.  The HB kernel's first launch is
-            // limited to that many CTAs per SM, so it can never occupy the whole device while it waits for operating points
-            // (an SM with fused_per_sm of them implies another with room to spare): DC warps can always become resident,
-            // whatever order the hardware places the two grids in.
-            int regs_sm = 0, smem_sm = 0;
-            YHB_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
-            YHB_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-            cudaFuncAttributes da;
-            const int Mdc = d.N + pl->num_inductors;
-            if (Mdc <= 12) YHB_CUDA(cudaFuncGetAttributes(&da, k_dc_warp<12>));
-            else YHB_CUDA(cudaFuncGetAttributes(&da, k_dc_warp<24>));
-            const long regs_left = (long)regs_sm - (long)(fused_per_sm - 1) * fa.numRegs * fused_threads(L.fc.NT);
-            const long smem_left = (long)smem_sm - (long)(fused_per_sm - 1) * ((long)L.fc.smem + (long)fa.sharedSizeBytes + 1024);
-            const long by_regs = regs_left / std::max(1, da.numRegs * 32);
-            const long by_smem = smem_left / (long)(dc_warp_smem(pl) + da.sharedSizeBytes + 1024);
-            dc_warps = (int)std::max(0l, std::min(by_regs, by_smem));
-            if (getenv("YHB_DEBUG"))
-                fprintf(stderr, "yhb: DC beside the HB kernel: room for %d warps per SM (registers allow %ld, shared memory %ld)\n",
-                        dc_warps, by_regs, by_smem);
-        }
+        overlap = dco && !no_overlap && dc_one_warp(pl);
     }
     const int *leader = nullptr;
     if (dco) {
@@ -1398,7 +1382,7 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
         ws.use_order = 1;
         ws.dc_valid = 1;
         if (dco->Vdc) ws.dcV = dco->Vdc;
-        if (dc_warps > 0) {
+        if (overlap) {
             if (!pl->dc_stream) {
                 int lo = 0, hi = 0;
                 YHB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1409,42 +1393,36 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
             ws.dc_wait = 1;
             YHB_CUDA(cudaMemsetAsync(ws.dc_ready, 0, sizeof(int) * ((size_t)B + 8), st));
         }
-        leader = dc_groups(pl, p, L, st, dc_warps > 0);  // before the fork: the HB kernel reads the leaders too
+        leader = dc_groups(pl, p, L, st, overlap);  // before the fork: the HB kernel reads the leaders too
     }
     if (int rc = launch_prepare(pl, p, L, st)) return rc;
-    if (dco && dc_warps == 0)  // no room beside the HB kernel (or the general DC engine): DC first, on the same stream
+    if (dco && !overlap)  // DC first, on the same stream
         if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, nullptr, nullptr, st, leader)) return rc;
     {
         ProfScope ps(PK_INIT, st);
         k_init<<<B, 128, 0, st>>>(d, ws, have_v0, alpha_fixed);
     }
     YHB_CUDA(cudaGetLastError());
-    if (dc_warps > 0) {  // fork: the DC kernel on the high-priority stream, in the HB kernel's work order
+    if (overlap) {  // fork: the DC kernel on the high-priority stream, in the HB kernel's work order; then the gate
         YHB_CUDA(cudaEventRecord(pl->ev_fork, st));
         YHB_CUDA(cudaStreamWaitEvent(pl->dc_stream, pl->ev_fork, 0));
         if (int rc = dc_launch(pl, p, L, ws.dcV, dco->info, ws.order, ws.dc_ready, pl->dc_stream, leader)) return rc;
+        YHB_CUDA(cudaEventRecord(pl->ev_join, pl->dc_stream));
+        k_dc_gate<<<1, 1, 0, st>>>(ws.dc_ready + B + 3, ws.dc_ready + B + 5);
+        YHB_CUDA(cudaGetLastError());
     }
     EvalArgs ea = eval_args(pl, p, opt, L);
     if (L.fused) {
         // persistent CTAs pulling circuits from a queue: grid = resident CTAs per SM x SMs
-        const int full = fused_per_sm * sms;
-        const int grid = std::min(B, dc_warps > 0 ? (fused_per_sm - 1) * sms : full);
+        const int grid = std::min(B, fused_per_sm * sms);
         if (getenv("YHB_DEBUG"))
-            fprintf(stderr, "yhb: k_fused<%d> threads %d smem %d B, %d CTAs/SM, grid %d, block-sparse %d\n", L.fc.NT,
-                    fused_threads(L.fc.NT), (int)L.fc.smem, fused_per_sm, grid, d.bs_ok);
+            fprintf(stderr, "yhb: k_fused<%d> threads %d smem %d B, %d CTAs/SM, grid %d, block-sparse %d, DC beside it %d\n", L.fc.NT,
+                    fused_threads(L.fc.NT), (int)L.fc.smem, fused_per_sm, grid, d.bs_ok, (int)overlap);
         {
             ProfScope ps(PK_FUSED, st);
             if (int rc = fused_launch(L.fc.NT, grid, (int)L.fc.smem, st, d, ws, ea, L.fc.hot)) return rc;
         }
-        if (dc_warps > 0) {
-            // when the DC kernel has finished, the last CTA per SM of the HB kernel moves in (second launch, on the DC
-            // stream, same work queue); join: Vdc / dc_info are complete for the caller
-            const int more = std::min(std::max(B - grid, 0), full - grid);
-            if (more > 0)
-                if (int rc = fused_launch(L.fc.NT, more, (int)L.fc.smem, pl->dc_stream, d, ws, ea, L.fc.hot)) return rc;
-            YHB_CUDA(cudaEventRecord(pl->ev_join, pl->dc_stream));
-            YHB_CUDA(cudaStreamWaitEvent(st, pl->ev_join, 0));
-        }
+        if (overlap) YHB_CUDA(cudaStreamWaitEvent(st, pl->ev_join, 0));  // join: Vdc / dc_info are complete for the caller
         return launch_finish(pl, L, res, st);
     }
     const int smem = eval_smem_bytes(pl, L);

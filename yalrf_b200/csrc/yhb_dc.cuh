@@ -45,6 +45,7 @@ struct DcArgs {
     const int *order;      // [B] or nullptr
     int *ready;            // [B] or nullptr
     int *nready;           // counter of solved circuits (with ready) or nullptr
+    int *nstarted;         // counter of circuits whose CTA has begun (with ready; the gate of yhb_solve_cold) or nullptr
     // circuits with bit-identical DC inputs (an amplitude sweep repeats every bias point): leader[b] = first circuit of
     // b's group (k_dc_group); only leaders are solved, k_dc_scatter copies their results to the others
     const int *leader;     // [B] or nullptr
@@ -753,6 +754,7 @@ __global__ void __launch_bounds__(32, YHB_DC_WARP_MINBLOCKS) k_dc_warp(PlanDev P
     if ((int)blockIdx.x >= batch) return;
     const int b = a.order ? a.order[blockIdx.x] : blockIdx.x;
     if (a.leader && a.leader[b] != b) return;
+    if (a.nstarted && lane == 0) atomicAdd(a.nstarted, 1);
     int *tab = reinterpret_cast<int *>(smw + (size_t)M * M + M + (size_t)kDcOut * max(a.nnl, 1) + (size_t)M * ((M + 1) | 1));
     for (int i = lane; i < a.ent_ints; i += 32) tab[i] = a.ent_tab[i];
     DcWarp<MMAX> w;
@@ -924,24 +926,47 @@ __global__ void __launch_bounds__(128) k_dc_hash(PlanDev P, DcArgs a, int batch,
     if (lane == 0) hash[b] = h;
 }
 
-// leader[b] = the first circuit of b's chunk (kDcGroupChunk circuits) whose DC inputs equal b's bit for bit
+// leader[b] = the first circuit of b's chunk (kDcGroupChunk circuits) whose DC inputs equal b's bit for bit; kDcGroupLanes
+// lanes share the scan of one circuit's chunk (strided), the smallest match wins
 constexpr int kDcGroupChunk = 8192;
+constexpr int kDcGroupLanes = 16;
 __global__ void __launch_bounds__(256) k_dc_group(PlanDev P, DcArgs a, int batch, const unsigned long long *hash, int *leader,
                                                   int *nlead) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= batch) return;
-    const int c0 = b / kDcGroupChunk * kDcGroupChunk;
-    const unsigned long long hb = hash[b];
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = g / kDcGroupLanes, sub = g % kDcGroupLanes;
+    const bool live = b < batch;
+    const int bb = live ? b : batch - 1;
+    const int c0 = bb / kDcGroupChunk * kDcGroupChunk;
+    const unsigned long long hb = hash[bb];
     const int nw = dc_words(P);
-    int lead = b;
-    for (int j = c0; j < b; ++j) {
+    int lead = bb;
+    for (int j = c0 + sub; j < bb; j += kDcGroupLanes) {
         if (hash[j] != hb) continue;
         bool same = true;
-        for (int i = 0; i < nw && same; ++i) same = dc_word(P, a, j, i) == dc_word(P, a, b, i);
+        for (int i = 0; i < nw && same; ++i) same = dc_word(P, a, j, i) == dc_word(P, a, bb, i);
         if (same) { lead = j; break; }
     }
-    leader[b] = lead;
-    if (nlead && lead == b) atomicAdd(nlead, 1);
+#pragma unroll
+    for (int o = kDcGroupLanes / 2; o > 0; o >>= 1) lead = min(lead, __shfl_xor_sync(0xffffffffu, lead, o));
+    if (live && sub == 0) {
+        leader[b] = lead;
+        if (nlead && lead == b) atomicAdd(nlead, 1);
+    }
+}
+
+// Gate between the DC kernel (side stream) and the HB kernel of an overlapped cold solve: opens when every DC problem's
+// CTA has begun, i.e. is resident or done -- HB CTAs, which wait for operating points, can then never keep a DC CTA off
+// the device -- and the DC kernel's long tail (its slowest circuits) runs beside the HB kernel.  More DC problems than
+// fit the device at once: the gate opens when the last wave has started.  Measured on the DiffAmp sweep (4096 circuits;
+// 64 / 256 / 1024 / 4096 distinct bias points): 15.8 / 16.9 / 17.1 / 34.6 ms against 17.1 / 19.4 / 19.0 / 42.0 ms with
+// the DC kernel in front of the HB kernel.
+__global__ void k_dc_gate(const int *nlead, const int *nstarted) {
+    const long long t0 = clock64();
+    const int n = *reinterpret_cast<const volatile int *>(nlead);
+    while (*reinterpret_cast<const volatile int *>(nstarted) < n) {
+        __nanosleep(500);
+        if (clock64() - t0 > 4000000000ll) break;  // seconds: the DC kernel never ran; the HB kernel has its own time-out
+    }
 }
 
 // results of the leaders to the other circuits of their groups
