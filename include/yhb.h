@@ -203,7 +203,8 @@ int yhb_plan_freqs(const yhb_plan *plan, double f1, double f2, double *freqs /* 
 size_t yhb_workspace_bytes(const yhb_plan *plan, int32_t batch);
 
 /* calc_V0 (:697-704) = DC.run (DC.py:54-123): batched DC operating points, Vdc[B][N] node voltages.
- * dc_info[B][2] = (converged, Newton iterations). */
+ * dc_info[B][2] = (converged, Newton iterations).  Circuits with bit-identical DC inputs are solved once (see
+ * yhb_solve_cold); every circuit of such a group reports the group's results. */
 int yhb_dc_solve(const yhb_plan *plan, const yhb_params *p, void *ws, size_t ws_bytes, double *Vdc,
                  int32_t *dc_info, void *stream);
 
@@ -215,12 +216,18 @@ int yhb_dc_solve(const yhb_plan *plan, const yhb_params *p, void *ws, size_t ws_
 int yhb_solve(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt, void *ws,
               size_t ws_bytes, int32_t have_v0, const double *Vdc, const yhb_result *res, void *stream);
 
-/* Cold run() as ONE call: calc_V0 (:321-324 -> DC.run) and the source-stepping ladder (:338-384).  On the fused (on-chip)
- * engine the batched DC analysis runs BESIDE the harmonic-balance kernel -- on a high-priority side stream of the plan,
- * forked from and joined into `stream` by events; the HB kernel takes the circuits in the DC kernel's order (strongest
- * drive first, so that its last wave of circuits is the cheapest) and waits for each operating point -- instead of in
- * front of it; the staged engines run the two one after the other.  Vdc[B][N] / dc_info[B][2] (optional outputs) as in
- * yhb_dc_solve.  A circuit whose operating point never arrived reports converged = -2. */
+/* Cold run() as ONE call: calc_V0 (:321-324 -> DC.run) and the source-stepping ladder (:338-384).  Circuits of the batch
+ * whose DC inputs are bit-identical (linear element values, DC source values, device parameters: the points of an
+ * amplitude or frequency sweep that share a bias point) share ONE DC analysis.  On the fused (on-chip) engine the DC
+ * kernel -- one warp per distinct DC problem, as long as its slowest circuit -- runs BESIDE the harmonic-balance kernel:
+ * on a high-priority side stream of the plan, forked from and joined into `stream` by events; a small gate kernel on
+ * `stream` holds the HB kernel back until every DC problem's CTA has begun (so that waiting HB CTAs can never keep DC
+ * work off the device); the HB kernel takes the circuits strongest drive first (its last wave of circuits is the
+ * cheapest), passes over circuits whose operating point has not arrived yet and serves them last.  The staged engines
+ * run DC and HB one after the other.  Vdc[B][N] / dc_info[B][2] (optional outputs) as in yhb_dc_solve.  A circuit whose
+ * operating point never arrived (the DC kernel did not run within seconds) reports converged = -2.
+ * The staged engines' solve loops synchronise `stream` once per Newton round (they size the next launches from the
+ * number of active circuits); the fused engine does not synchronise. */
 int yhb_solve_cold(const yhb_plan *plan, const yhb_params *p, const yhb_options *opt, void *ws, size_t ws_bytes,
                    double *Vdc, int32_t *dc_info, const yhb_result *res, void *stream);
 

@@ -109,6 +109,38 @@ def gather_packed(local, B, group=None):
     return rows[b % world, b // world]     # circuit b = row b // world of rank b % world
 
 
+def gather_unpack_device(plan, local, B, lay, group=None):
+    """NCCL path: local = this rank's [n][R] rows in HBM.  ONE all_gather_into_tensor, the rows put into circuit order
+    by one device copy (circuit b = row b // world of rank b % world: a transpose of the [world][nmax] row grid), every
+    field split off on the device and copied straight into the page-locked arrays of the BatchResult -- no host-side
+    repacking of the gathered results."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    nmax = shard_count(B, 0, world)
+    R = lay.R
+    t = local
+    if t.shape[0] < nmax:  # ranks with one circuit less: pad to the common row count
+        t = torch.cat([t, torch.zeros((nmax - t.shape[0], R), dtype=t.dtype, device=t.device)])
+    out = torch.empty((world * nmax, R), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    rows = out.view(world, nmax, R).transpose(0, 1).reshape(world * nmax, R)[:B]      # circuit order
+    full = BatchResult(plan, B, pinned=True, levels=lay.levels)
+    keep = []
+    for name, _ in lay.fields:
+        lo, hi = lay.off[name]
+        dst = getattr(full, name)
+        col = rows[:, lo:hi]
+        if dst.dtype == np.int32:
+            col = col.to(torch.int32)               # exact: the reports were packed from int32
+        col = col.contiguous()
+        keep.append(col)
+        host = torch.from_numpy(dst.view(np.float64) if np.iscomplexobj(dst) else dst).reshape(B, -1)
+        host.copy_(col.reshape(B, -1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return full
+
+
 def run_block_distributed(plan, pb, options, V0=None, group=None, run_fn=None, levels=True):
     """Solve this rank's circuits of the block and gather.  run_fn(plan, pb, options, V0) -> BatchResult (host) is
     for tests; the default keeps parameters and results in HBM (DeviceBatch) and packs / gathers on the device."""
@@ -133,4 +165,6 @@ def run_block_distributed(plan, pb, options, V0=None, group=None, run_fn=None, l
             db.V.copy_(torch.from_numpy(v0))
             db.solve(options, have_v0=True, with_dc=True)
         local = pack_device(db, lay)
+        if dist.get_backend(group) == 'nccl':
+            return gather_unpack_device(plan, local, pb.B, lay, group)
     return unpack(plan, gather_packed(local, pb.B, group), lay)
