@@ -713,6 +713,39 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
         }
     d.nA = (int)a_row.size();
     d.nB = (int)b_row.size();
+    // Steps that do not read each other's result run side by side: an A step reads the columns fixed by earlier A steps
+    // among its row's other entries; a B step (processed in reverse order of discovery) reads the columns recovered by
+    // B steps processed before it.  Steps are stable-sorted by level; the B lists are stored in processing order.
+    std::vector<int> a_lev(1, 0), b_lev(1, 0);
+    {
+        auto by_level = [&](std::vector<int> &row, std::vector<int> &col, std::vector<int> &sgn, std::vector<int> &lev_ptr) {
+            const int n = (int)row.size();
+            std::vector<int> made(N, -1), level(n, 0), perm(n);
+            for (int i = 0; i < n; ++i) {
+                int lv = 0;
+                for (int p : row_cols[row[i]]) {
+                    const int m = pairs[p].second;
+                    if (m != col[i] && made[m] >= 0) lv = std::max(lv, level[made[m]] + 1);
+                }
+                level[i] = lv;
+                made[col[i]] = i;
+                perm[i] = i;
+            }
+            std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return level[x] < level[y]; });
+            std::vector<int> r2(n), c2(n), s2(n);
+            for (int i = 0; i < n; ++i) { r2[i] = row[perm[i]]; c2[i] = col[perm[i]]; s2[i] = sgn[perm[i]]; }
+            row = r2; col = c2; sgn = s2;
+            for (int i = 0; i < n; ++i)
+                if (i + 1 == n || level[perm[i + 1]] != level[perm[i]]) lev_ptr.push_back(i + 1);
+        };
+        by_level(a_row, a_col, a_sgn, a_lev);
+        std::reverse(b_row.begin(), b_row.end());
+        std::reverse(b_col.begin(), b_col.end());
+        std::reverse(b_sgn.begin(), b_sgn.end());
+        by_level(b_row, b_col, b_sgn, b_lev);
+    }
+    d.nAlev = (int)a_lev.size() - 1;
+    d.nBlev = (int)b_lev.size() - 1;
     std::vector<int> a_ptr(1, 0), a_pair, a_m, b_ptr(1, 0), b_pair, b_m, r_ptr(1, 0), r_pair, r_m;
     for (int a = 0; a < d.nA; ++a) {  // the other entries of an A row (all A-known by construction)
         for (int p : row_cols[a_row[a]])
@@ -803,6 +836,7 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     UP(core_rows, core_rows); UP(core_cols, core_cols); UP(core_col_of, core_col_of);
     UP(a_row, a_row); UP(a_col, a_col); UP(a_sgn, a_sgn); UP(a_ptr, a_ptr); UP(a_pair, a_pair); UP(a_m, a_m);
     UP(b_row, b_row); UP(b_col, b_col); UP(b_sgn, b_sgn); UP(b_ptr, b_ptr); UP(b_pair, b_pair); UP(b_m, b_m);
+    UP(a_lev, a_lev); UP(b_lev, b_lev);
     UP(r_ptr, r_ptr); UP(r_pair, r_pair); UP(r_m, r_m);
     UP(bs_order, bs_order); UP(bs_pos, bs_pos); UP(bs_level_ptr, bs_level_ptr); UP(bs_rowbase, bs_rowbase);
     UP(bs_ld, bs_ld); UP(bs_nlater, bs_nlater); UP(bs_nblk, bs_nblk); UP(bs_rhsoff, bs_rhsoff);

@@ -66,6 +66,7 @@ struct PlanDev {
     // B-steps (column singletons): the same formula, evaluated in REVERSE order after the core solve.
     // Core: J[core_rows, core_cols] y = F[core_rows] - sum_{A-known m} J[row, m] dV[m].
     int Nc, Wc, nA, nB;
+    int nAlev, nBlev;  // levels of mutually independent A / B steps (a_lev / b_lev: [levels + 1] step ranges)
     int band;  // > 0: the core is block banded over nodes; kl = ku = band (in matrix elements), band storage
     int btd;   // the core is block TRIdiagonal over nodes and is solved block by block (block-Thomas engine): the
                // Jacobian is stored as Nc x 3 column-major S x S blocks (sub-diagonal, diagonal, super-diagonal)
@@ -73,7 +74,8 @@ struct PlanDev {
     const int *core_col_of;            // [N] -> position among core_cols or -1
     const int *a_row, *a_col, *a_sgn;  // [nA]
     const int *a_ptr, *a_pair, *a_m;   // other entries of each A row: CSR [nA+1], pair index, column node
-    const int *b_row, *b_col, *b_sgn;  // [nB]
+    const int *b_row, *b_col, *b_sgn;  // [nB], in the order the steps are processed
+    const int *a_lev, *b_lev;
     const int *b_ptr, *b_pair, *b_m;
     const int *r_ptr, *r_pair, *r_m;   // per core row: entries in A-known columns, CSR [Nc+1]
     // ---- block-sparse LU of the core over node blocks (bs_ok): the core is stored as Nc block ROWS, block row k =
@@ -105,7 +107,7 @@ struct PlanDev {
     X(idft) X(dft) X(diode_nodes) X(bjt_nodes) X(cubic_nodes) X(dev_wave_base) X(pair_n) X(pair_m) X(pair_of) \
     X(row_ptr) X(row_pairs) X(pg_ptr) X(pg) X(pc_ptr) X(pc) X(ni_ptr) X(ni) X(nq_ptr) X(nq) X(core_rows)      \
     X(core_cols) X(core_col_of) X(a_row) X(a_col) X(a_sgn) X(a_ptr) X(a_pair) X(a_m) X(b_row) X(b_col)        \
-    X(b_sgn) X(b_ptr) X(b_pair) X(b_m) X(r_ptr) X(r_pair) X(r_m) X(bs_order) X(bs_pos) X(bs_level_ptr) X(bs_rowbase)      \
+    X(b_sgn) X(b_ptr) X(b_pair) X(b_m) X(a_lev) X(b_lev) X(r_ptr) X(r_pair) X(r_m) X(bs_order) X(bs_pos) X(bs_level_ptr) X(bs_rowbase)      \
     X(bs_ld) X(bs_nlater) X(bs_nblk) X(bs_rhsoff) X(bs_coloff) X(bs_blkof) X(bs_below_ptr) X(bs_below) X(cblk)
 
 struct Plan {
