@@ -585,7 +585,7 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     // ---- block-sparse LU structure of the core (PlanDev::bs_*): ordering by levels of independent minimum-degree
     // nodes, fill, block-row storage map
     std::vector<int> bs_order, bs_pos, bs_level_ptr(1, 0), bs_rowbase, bs_ld, bs_nlater, bs_nblk, bs_rhsoff, bs_coloff,
-        bs_blkof, bs_below_ptr(1, 0), bs_below;
+        bs_blkof, bs_below_ptr(1, 0), bs_below, bs_lev_uniform;
     d.bs_ok = 0;
     d.bs_nlev = 0;
     d.bs_total = 0;
@@ -692,6 +692,20 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
                 for (int i = 0; i < Nc; ++i)
                     if (bs_pos[i] > bs_pos[k] && nz[i][k]) bs_below.push_back(i);
                 bs_below_ptr.push_back((int)bs_below.size());
+            }
+            for (size_t lev = 0; lev + 1 < bs_level_ptr.size(); ++lev) {
+                bool uni = true;
+                const int k0 = bs_order[bs_level_ptr[lev]];
+                for (int t = bs_level_ptr[lev] + 1; t < bs_level_ptr[lev + 1] && uni; ++t) {
+                    const int k = bs_order[t];
+                    uni = bs_nlater[k] == bs_nlater[k0] &&
+                          bs_below_ptr[k + 1] - bs_below_ptr[k] == bs_below_ptr[k0 + 1] - bs_below_ptr[k0];
+                    for (int sl = 0; uni && sl < bs_nlater[k0]; ++sl)
+                        uni = bs_blkof[(size_t)k * Nc + 1 + sl] == bs_blkof[(size_t)k0 * Nc + 1 + sl];
+                    for (int q = 0; uni && q < bs_below_ptr[k0 + 1] - bs_below_ptr[k0]; ++q)
+                        uni = bs_below[bs_below_ptr[k] + q] == bs_below[bs_below_ptr[k0] + q];
+                }
+                bs_lev_uniform.push_back(uni && bs_level_ptr[lev + 1] - bs_level_ptr[lev] > 1 ? 1 : 0);
             }
             const bool sparse = nnz1 < Nc * Nc;
             // never more than the dense matrix of the fused engine
@@ -841,6 +855,7 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     UP(bs_order, bs_order); UP(bs_pos, bs_pos); UP(bs_level_ptr, bs_level_ptr); UP(bs_rowbase, bs_rowbase);
     UP(bs_ld, bs_ld); UP(bs_nlater, bs_nlater); UP(bs_nblk, bs_nblk); UP(bs_rhsoff, bs_rhsoff);
     UP(bs_coloff, bs_coloff); UP(bs_blkof, bs_blkof); UP(bs_below_ptr, bs_below_ptr); UP(bs_below, bs_below);
+    UP(bs_lev_uniform, bs_lev_uniform);
     d.blob_hot_bytes = (int)align_up(blob.size(), 16);
     // k_prepare / k_dc only
     UP(bin_k1, pl->bin_k1);

@@ -92,6 +92,8 @@ struct PlanDev {
     const int *bs_ld;         // [Nc] leading dimension of block row k (odd)
     const int *bs_below_ptr;  // [Nc + 1] CSR over bs_below
     const int *bs_below;      // block rows i (eliminated after k) that hold a block (i, k)
+    const int *bs_lev_uniform;  // [bs_nlev] all nodes of the level have the same later blocks and the same rows below:
+                                // their Schur updates hit the same target tiles and are applied in one pass
     const int *bs_nlater;     // [Nc] blocks (k, j) with j eliminated after k
     const int *bs_nblk;       // [Nc] blocks in block row k (diagonal included); rhs column = S * bs_nblk[k]... see bs_rhsoff
     const int *bs_rhsoff;     // [Nc] column of rhs_k in block row k
@@ -108,7 +110,7 @@ struct PlanDev {
     X(row_ptr) X(row_pairs) X(pg_ptr) X(pg) X(pc_ptr) X(pc) X(ni_ptr) X(ni) X(nq_ptr) X(nq) X(core_rows)      \
     X(core_cols) X(core_col_of) X(a_row) X(a_col) X(a_sgn) X(a_ptr) X(a_pair) X(a_m) X(b_row) X(b_col)        \
     X(b_sgn) X(b_ptr) X(b_pair) X(b_m) X(a_lev) X(b_lev) X(r_ptr) X(r_pair) X(r_m) X(bs_order) X(bs_pos) X(bs_level_ptr) X(bs_rowbase)      \
-    X(bs_ld) X(bs_nlater) X(bs_nblk) X(bs_rhsoff) X(bs_coloff) X(bs_blkof) X(bs_below_ptr) X(bs_below) X(cblk)
+    X(bs_ld) X(bs_nlater) X(bs_nblk) X(bs_rhsoff) X(bs_coloff) X(bs_blkof) X(bs_below_ptr) X(bs_below) X(bs_lev_uniform) X(cblk)
 
 struct Plan {
     PlanDev d;                  // device view
