@@ -1,9 +1,8 @@
-# BASELINE config 5 (ladder, block-Thomas engine): reductions with Cje = 1e-12 + exact Jacobian (convergence check), then the
-# full size (256 stages, [16,16]) as a single ladder and as a batch of jittered ladders.  Every run under its own timeout.
+# BASELINE config 5 (ladder, block-Thomas engine): parity tests of the engine, then the full size (256 stages, [16,16],
+# Cje = 0: see DESIGN section 5) as a single ladder and as batches of jittered ladders.  Every run under its own timeout.
 TAG=${TAG:-lad}
-timeout 100 python scripts/bench_ladder.py 256 2 2 1e-12 0.5 1 1 > gpurun_out/${TAG}_ladder256_2x2_cje.log 2>&1; tail -5 gpurun_out/${TAG}_ladder256_2x2_cje.log
-timeout 100 python scripts/bench_ladder.py 32 4 4 1e-12 0.5 1 1 > gpurun_out/${TAG}_ladder32_4x4_cje.log 2>&1; tail -5 gpurun_out/${TAG}_ladder32_4x4_cje.log
-for b in ${BATCHES:-4}; do
+python -m pytest tests -m gpu -x -q -k "ladder or gjp or engines_agree" > gpurun_out/${TAG}_tests.log 2>&1; tail -3 gpurun_out/${TAG}_tests.log
+for b in ${BATCHES:-1 4}; do
   timeout ${LADDER_TIMEOUT:-150} python scripts/bench_ladder.py 256 16 16 0 0.5 0 $b > gpurun_out/${TAG}_ladder_b$b.log 2>&1
   tail -5 gpurun_out/${TAG}_ladder_b$b.log
 done

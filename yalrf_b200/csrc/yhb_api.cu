@@ -1066,15 +1066,16 @@ Layout carve(const yhb_plan *pl, int B, void *base) {
     ws.pairwav = c.take<double>((size_t)B * std::max(d.npair_nl, 1) * 2 * S);
     ws.gj_n = gjn;
     ws.gj_lpad = (gjn + 7) & ~7;
-    ws.gj_L = c.take<double>(gjn ? (size_t)B * kGjpNB * ws.gj_lpad : 1);
+    const size_t Bs = (size_t)B * (d.btd ? 2 : 1);  // the block-Thomas engine runs two systems per circuit (both chain ends)
+    ws.gj_L = c.take<double>(gjn ? Bs * kGjpNB * ws.gj_lpad : 1);
     ws.gj_ld = !gjn ? 0 : (d.btd ? btd_ldm(d.S) : gjp_dense_ld(d.Wc));
-    ws.gj_U = c.take<double>(gjn ? (size_t)B * kGjpNB * ws.gj_ld : 1);
-    ws.gj_T = c.take<double>((size_t)B * kGjpNB * kGjpNB);
-    ws.gj_piv = c.take<double>(gjn ? (size_t)B * gjn : 1);
-    ws.gj_rowof = c.take<int>(gjn ? (size_t)B * gjn : 1);
-    ws.gj_used = c.take<int>(gjn ? (size_t)B * gjn : 1);
-    ws.gj_pp = c.take<int>((size_t)B * kGjpNB);
-    ws.gj_fail = c.take<int>(B);
+    ws.gj_U = c.take<double>(gjn ? Bs * kGjpNB * ws.gj_ld : 1);
+    ws.gj_T = c.take<double>(Bs * kGjpNB * kGjpNB);
+    ws.gj_piv = c.take<double>(gjn ? Bs * gjn : 1);
+    ws.gj_rowof = c.take<int>(gjn ? Bs * gjn : 1);
+    ws.gj_used = c.take<int>(gjn ? Bs * gjn : 1);
+    ws.gj_pp = c.take<int>(Bs * kGjpNB);
+    ws.gj_fail = c.take<int>(Bs);
     ws.Inl = nullptr;
     ws.Ic = nullptr;
     ws.skip = nullptr;
@@ -1231,17 +1232,25 @@ GjpBatch gjp_batch(const Workspace &ws, const int *list) {
 }
 
 // Block-Thomas elimination of the queued circuits' block-tridiagonal cores (blocks as k_assemble_btd laid them out;
-// right-hand sides in the block rows, solution into ws.rhs), all circuits concurrently:
-//   forward, block row r:  [D_r | rhs_r] -= L_r [U'_{r-1} | b'_{r-1}]              (k_btd_schur: DMMA GEMM + GEMV)
-//                          Gauss-Jordan of [D_r | U_r | rhs_r] with partial pivoting inside D_r (gjp_run)
-//                          U'_r = D_r^-1 U_r -> storage of L_r,  b'_r = D_r^-1 rhs_r -> ws.rhs     (k_gjp_finish)
-//   backward:              x_r = b'_r - U'_r x_{r+1}                                               (k_btd_back)
+// right-hand sides in the block rows, solution into ws.rhs), all circuits concurrently and every chain from BOTH ends
+// towards the middle block row mid (two block rows per circuit in every launch: half the serial depth):
+//   elimination step j:    upper chain r = j, lower chain r = Nc - 1 - j (inner neighbour q = r + 1 / r - 1):
+//                          [D_r | rhs_r] -= side(r) [X'_prev | b'_prev]                  (k_btd_schur: DMMA GEMM + GEMV)
+//                          Gauss-Jordan of [D_r | carried(r) | rhs_r], pivoting inside D_r (gjp_run)
+//                          X'_r = D_r^-1 carried(r) -> side storage,  b'_r = D_r^-1 rhs_r -> ws.rhs   (k_gjp_finish)
+//   middle row:            one update from each side, then x_mid = D_mid^-1 rhs_mid
+//   back substitution:     x_r = b'_r - X'_r x_q outwards from the middle, both chains per launch     (k_btd_back)
 int block_thomas_solve(const PlanDev &d, const Workspace &ws, const int *list, int nsolve, cudaStream_t st) {
-    const int S = d.S, Nc = d.Nc;
+    const int S = d.S, Nc = d.Nc, mid = btd_mid(Nc);
+    const int nup = mid, nlo = Nc - 1 - mid;  // rows of the upper / lower chain
+    const size_t rowd = btd_row_doubles(S);
     GjpBatch g = gjp_batch(ws, list);
     g.ld = btd_ldm(S);
     g.ncols = gjp_npc(S) + S + 1;
+    g.npos = nsolve;
+    g.vs_stride = ws.batch;
     SchurArgs sa;
+    memset(&sa, 0, sizeof(sa));
     sa.J = ws.J;
     sa.j_stride = ws.j_stride;
     sa.rhs = ws.rhs;
@@ -1249,32 +1258,72 @@ int block_thomas_solve(const PlanDev &d, const Workspace &ws, const int *list, i
     sa.list = list;
     sa.count = nullptr;
     sa.S = S;
+    sa.npos = nsolve;
     const int ntx = (S + kSchurBN - 1) / kSchurBN, nty = (S + kSchurBM - 1) / kSchurBM;
-    for (int r = 0; r < Nc; ++r) {
-        if (r > 0) {
-            sa.r = r;
-            k_btd_schur<<<dim3(ntx + 1, nty, nsolve), 256, 0, st>>>(sa);
-        }
-        g.m_off = (size_t)r * btd_row_doubles(S);
-        if (int rc = gjp_run(g, nsolve, st)) return rc;
+    const int nfin = std::min((S + 7) / 8, 148);
+    // one Gauss-Jordan pass over block rows r0 (and r1 if >= 0); next: the carried block becomes X' in the side storage
+    auto eliminate = [&](int r0, int r1, bool want_x) -> int {
+        g.nchain = r1 >= 0 ? 2 : 1;
+        g.m_off = (size_t)r0 * rowd;
+        g.m_off2 = r1 >= 0 ? (size_t)r1 * rowd : 0;
+        if (int rc = gjp_run(g, g.nchain * nsolve, st)) return rc;
         GjpFinish f;
         memset(&f, 0, sizeof(f));
-        if (r + 1 < Nc) {
+        if (want_x) {
             f.out0 = ws.J;
             f.out0_stride = ws.j_stride;
             f.out0_off = g.m_off + (size_t)S * btd_ldm(S);
+            f.out0_off2 = g.m_off2 + (size_t)S * btd_ldm(S);
             f.nout0 = S;
             f.ld0 = btd_lds(S);
         }
         f.out1 = ws.rhs;
         f.out1_stride = (size_t)d.Wc + 1;
-        f.out1_off = (size_t)r * S;
+        f.out1_off = (size_t)r0 * S;
+        f.out1_off2 = r1 >= 0 ? (size_t)r1 * S : 0;
         f.col1 = S;
-        k_gjp_finish<<<dim3(std::min((S + 7) / 8, 148), nsolve), 256, 0, st>>>(g, f);
+        k_gjp_finish<<<dim3(nfin, g.nchain * nsolve), 256, 0, st>>>(g, f);
+        return 0;
+    };
+    const int steps = std::max(nup, nlo);
+    for (int j = 0; j < steps; ++j) {
+        const int ru = j < nup ? j : -1, rl = j < nlo ? Nc - 1 - j : -1;
+        const int r0 = ru >= 0 ? ru : rl, r1 = (ru >= 0 && rl >= 0) ? rl : -1;
+        if (j > 0) {
+            sa.nchain = r1 >= 0 ? 2 : 1;
+            sa.r[0] = r0;
+            sa.rprev[0] = r0 == ru ? r0 - 1 : r0 + 1;
+            sa.a_in_m[0] = 0;
+            sa.r[1] = r1;
+            sa.rprev[1] = r1 + 1;
+            sa.a_in_m[1] = 0;
+            k_btd_schur<<<dim3(ntx + 1, nty, sa.nchain * nsolve), 256, 0, st>>>(sa);
+        }
+        if (int rc = eliminate(r0, r1, true)) return rc;
     }
-    for (int r = Nc - 2; r >= 0; --r) {
-        sa.r = r;
-        k_btd_back<<<dim3(std::min((S + 7) / 8, 148), nsolve), 256, 0, st>>>(sa);
+    // the middle row: the update from above, then the one from below (U_mid is the carried block of its Mr), the solve
+    sa.nchain = 1;
+    sa.r[0] = mid;
+    if (nup > 0) {
+        sa.rprev[0] = mid - 1;
+        sa.a_in_m[0] = 0;
+        k_btd_schur<<<dim3(ntx + 1, nty, nsolve), 256, 0, st>>>(sa);
+    }
+    if (nlo > 0) {
+        sa.rprev[0] = mid + 1;
+        sa.a_in_m[0] = 1;
+        k_btd_schur<<<dim3(ntx + 1, nty, nsolve), 256, 0, st>>>(sa);
+    }
+    if (int rc = eliminate(mid, -1, false)) return rc;
+    for (int dist = 1; dist <= steps; ++dist) {  // outwards: row mid - dist from mid - dist + 1, row mid + dist from mid + dist - 1
+        const int ru = mid - dist >= 0 ? mid - dist : -1, rl = mid + dist < Nc ? mid + dist : -1;
+        const int r0 = ru >= 0 ? ru : rl, r1 = (ru >= 0 && rl >= 0) ? rl : -1;
+        sa.nchain = r1 >= 0 ? 2 : 1;
+        sa.r[0] = r0;
+        sa.rprev[0] = r0 == ru ? r0 + 1 : r0 - 1;
+        sa.r[1] = r1;
+        sa.rprev[1] = r1 - 1;
+        k_btd_back<<<dim3(nfin, sa.nchain * nsolve), 256, 0, st>>>(sa);
     }
     YHB_CUDA(cudaGetLastError());
     return 0;

@@ -51,11 +51,32 @@ struct GjpBatch {
     const int *list;  // optional indirection (staged engine's active list) and its length
     const int *count;
     int n, ld, ncols, lpad;
+    // Two systems per circuit (the block-Thomas engine eliminates its chain from both ends): launch positions
+    // [0, npos) are the circuits' first systems (matrix at m_off), [npos, 2 npos) their second ones (matrix at m_off2);
+    // the scratch buffers (L, U, T, piv, rowof, used, pp, fail) of the second systems sit vs_stride systems further on.
+    int nchain, npos, vs_stride;
+    size_t m_off2;
 };
 
-__device__ __forceinline__ int gjp_system(const GjpBatch &g, int pos) {
-    if (g.count && pos >= *g.count) return -1;
-    return g.list ? g.list[pos] : pos;
+struct GjpSys {
+    int b;      // circuit (-1: nothing to do at this launch position)
+    int vs;     // index of the system's scratch buffers
+    int chain;  // 0 / 1
+};
+
+__device__ __forceinline__ GjpSys gjp_locate(const GjpBatch &g, int pos) {
+    int chain = 0;
+    if (g.nchain > 1 && pos >= g.npos) {
+        chain = 1;
+        pos -= g.npos;
+    }
+    if (g.count && pos >= *g.count) return GjpSys{-1, -1, 0};
+    const int b = g.list ? g.list[pos] : pos;
+    return GjpSys{b, b + chain * g.vs_stride, chain};
+}
+
+__device__ __forceinline__ double *gjp_matrix(const GjpBatch &g, const GjpSys &gs) {
+    return g.M + (size_t)gs.b * g.m_stride + (gs.chain ? g.m_off2 : g.m_off);
 }
 
 // warp-wide arg-max of (key_hi, key_lo) with ties to the lowest row; key_hi == 0 means "no candidate"
@@ -111,11 +132,12 @@ __global__ void __launch_bounds__(576, 1) k_gjp_panel(GjpBatch g, int j) {
     __shared__ int s_row[32];
     __shared__ double urow[2][kGjpNB];
     __shared__ int pps[kGjpNB];
-    const int sys = gjp_system(g, blockIdx.x);
-    if (sys < 0) return;
+    const GjpSys gs = gjp_locate(g, blockIdx.x);
+    if (gs.b < 0) return;
+    const int sys = gs.vs;  // scratch buffers
     const int n = g.n, ld = g.ld, lpad = g.lpad;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-    double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
+    double *M = gjp_matrix(g, gs);
     double *Lg = g.L + (size_t)sys * kGjpNB * lpad;
     int *used = g.used + (size_t)sys * n;
     const int col0 = j * kGjpNB;
@@ -217,11 +239,12 @@ __global__ void __launch_bounds__(1024, 1) k_gjp_panel_smem(GjpBatch g, int j) {
     __shared__ unsigned s_hi[2][32], s_lo[2][32];
     __shared__ int s_row[2][32];
     __shared__ int pps[kGjpNB];
-    const int sys = gjp_system(g, blockIdx.x);
-    if (sys < 0) return;
+    const GjpSys gs = gjp_locate(g, blockIdx.x);
+    if (gs.b < 0) return;
+    const int sys = gs.vs;  // scratch buffers
     const int n = g.n, ld = g.ld, npad = n | 1, lpad = g.lpad;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-    double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
+    double *M = gjp_matrix(g, gs);
     double *Lg = g.L + (size_t)sys * kGjpNB * lpad;
     int *used = g.used + (size_t)sys * n;
     const int col0 = j * kGjpNB;
@@ -306,14 +329,15 @@ constexpr int kGjpUpdCols = 32, kGjpUpdRows = 128;
 __global__ void __launch_bounds__(256) k_gjp_update(GjpBatch g, int j) {
     __shared__ double Ts[kGjpNB][kGjpNB];
     __shared__ double Us[kGjpNB][kGjpUpdCols + 4];
-    const int sys = gjp_system(g, blockIdx.z);
-    if (sys < 0) return;
+    const GjpSys gs = gjp_locate(g, blockIdx.z);
+    if (gs.b < 0) return;
+    const int sys = gs.vs;  // scratch buffers
     const int n = g.n, ld = g.ld, lpad = g.lpad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, t = lane & 3;
     const int c0 = (j + 1) * kGjpNB + kGjpUpdCols * blockIdx.x;
     const int r0 = kGjpUpdRows * blockIdx.y + 16 * warp;
-    double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
+    double *M = gjp_matrix(g, gs);
     const double *Lg = g.L + (size_t)sys * kGjpNB * lpad;
     const double *U = g.U + (size_t)sys * kGjpNB * ld;
     Ts[tid >> 4][tid & 15] = g.T[(size_t)sys * kGjpNB * kGjpNB + tid];
@@ -380,18 +404,19 @@ __global__ void __launch_bounds__(256) k_gjp_update(GjpBatch g, int j) {
 // carried block, [n][ld0] row-major (pad columns zeroed); out1 (optional): carried column col1 as a vector [n].
 struct GjpFinish {
     double *out0;
-    size_t out0_stride, out0_off;
+    size_t out0_stride, out0_off, out0_off2;  // per circuit; _off2: the circuits' second systems (GjpBatch::nchain)
     int nout0, ld0;
     double *out1;
-    size_t out1_stride, out1_off;
+    size_t out1_stride, out1_off, out1_off2;
     int col1;
 };
 
 __global__ void __launch_bounds__(256) k_gjp_finish(GjpBatch g, GjpFinish f) {
-    const int sys = gjp_system(g, blockIdx.y);
-    if (sys < 0) return;
+    const GjpSys gs = gjp_locate(g, blockIdx.y);
+    if (gs.b < 0) return;
+    const int sys = gs.vs;  // scratch buffers
     const int n = g.n, ld = g.ld;
-    const double *M = g.M + (size_t)sys * g.m_stride + g.m_off;
+    const double *M = gjp_matrix(g, gs);
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     const int fail = g.fail[sys];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -401,26 +426,34 @@ __global__ void __launch_bounds__(256) k_gjp_finish(GjpBatch g, GjpFinish f) {
         const bool bad = fail || r < 0;
         const double *src = M + (size_t)(bad ? 0 : r) * ld + gjp_npc(n);
         if (f.out0) {
-            double *dst = f.out0 + (size_t)sys * f.out0_stride + f.out0_off + (size_t)c * f.ld0;
+            double *dst = f.out0 + (size_t)gs.b * f.out0_stride + (gs.chain ? f.out0_off2 : f.out0_off) + (size_t)c * f.ld0;
             for (int k = lane; k < f.ld0; k += 32) dst[k] = k < f.nout0 ? (bad ? nan : src[k] / pv) : 0.;
         }
         if (f.out1 && lane == 0)
-            f.out1[(size_t)sys * f.out1_stride + f.out1_off + c] = bad ? nan : src[f.col1] / pv;
+            f.out1[(size_t)gs.b * f.out1_stride + (gs.chain ? f.out1_off2 : f.out1_off) + c] = bad ? nan : src[f.col1] / pv;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------- //
-// Block-Thomas engine: storage of one circuit's block-tridiagonal core (Nc block rows of S x S node blocks)
-//   block row r:  Mr [S][ldm]  = [ D_r | pad to npc = gjp_npc(S) | U_r (block (r, r+1)) | rhs_r | pad ]
-//                 Lr [S][lds]  = sub-diagonal block (r, r-1) (pad column zero), lds = S + (S & 1) + ... even;
-//                                after block row r is eliminated its storage holds U'_r = D_r^-1 U_r
+// Block-Thomas engine: storage of one circuit's block-tridiagonal core (Nc block rows of S x S node blocks).  The chain is
+// eliminated from BOTH ends towards the middle block row mid = Nc / 2 (two block rows in flight per circuit: half the
+// serial depth).  Upper rows r <= mid:
+//   Mr [S][ldm]  = [ D_r | pad to npc = gjp_npc(S) | U_r (block (r, r+1)) | rhs_r | pad ]
+//   Lr [S][lds]  = sub-diagonal block (r, r-1) (pad column zero); after block row r is eliminated this storage holds
+//                  U'_r = D_r^-1 U_r
+// Lower rows r > mid are stored mirrored -- Mr = [ D_r | pad | L_r | rhs_r | pad ], side slot = U_r, later L'_r = D_r^-1 L_r --
+// so that the same kernels run both chains: eliminating x_r from its inner neighbour's row is
+//   [D_q | rhs_q] -= (side slot of q) . [X'_r | b'_r],   q = r + 1 (upper chain) or r - 1 (lower chain).
+// The middle row takes one such update from each side (the one from below reads U_mid out of Mr's carried block).
 // ---------------------------------------------------------------------------------------------------------------- //
 __host__ __device__ inline int btd_ldm(int S) { return (gjp_npc(S) + S + 2) & ~1; }
 __host__ __device__ inline int btd_lds(int S) { return (S + 2) & ~1; }
 __host__ __device__ inline size_t btd_row_doubles(int S) { return (size_t)S * btd_ldm(S) + (size_t)S * btd_lds(S); }
+__host__ __device__ inline int btd_mid(int Nc) { return Nc / 2; }
 
-// C[S x S] (leading S columns of Mr) -= A (Lr, [S][lds]) . B (U'_{r-1}, [S][lds]);  rhs column -= A . x (b'_{r-1}).
+// C[S x S] (leading S columns of Mr) -= A ([S][lda]) . B (X'_prev, [S][lds]);  rhs column -= A . b'_prev.
 // 64 x 64 tiles, k slabs of 16 staged in shared memory by cp.async (double buffered), 8 warps of 16 x 32 outputs each.
+// Launch positions [0, npos) work on (r[0], rprev[0]), positions [npos, 2 npos) on (r[1], rprev[1]) (nchain = 2).
 constexpr int kSchurBM = 64, kSchurBN = 64, kSchurBK = 16;
 struct SchurArgs {
     double *J;        // circuit b at J + b * j_stride
@@ -428,8 +461,22 @@ struct SchurArgs {
     double *rhs;      // [B][Wc + 1]: b' of the eliminated block rows / rhs of the others
     size_t rhs_stride;
     const int *list, *count;
-    int S, r;         // block row being updated (r >= 1)
+    int S;
+    int nchain, npos;
+    int r[2];         // block row being updated (Schur) / substituted (back)
+    int rprev[2];     // the eliminated neighbour whose X' and b' (Schur) / the solved neighbour whose x (back) is used
+    int a_in_m[2];    // Schur: the coupling block A is the carried block of Mr ([S][ldm] at column npc) instead of the side slot
 };
+
+__device__ __forceinline__ int schur_locate(const SchurArgs &a, int pos, int &chain) {
+    chain = 0;
+    if (a.nchain > 1 && pos >= a.npos) {
+        chain = 1;
+        pos -= a.npos;
+    }
+    if (a.count && pos >= *a.count) return -1;
+    return a.list ? a.list[pos] : pos;
+}
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -440,26 +487,29 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, boo
 __global__ void __launch_bounds__(256) k_btd_schur(SchurArgs a) {
     __shared__ __align__(16) double As[2][kSchurBM][kSchurBK + 4];
     __shared__ __align__(16) double Bs[2][kSchurBK][kSchurBN + 4];
-    const int pos = blockIdx.z;
-    if (a.count && pos >= *a.count) return;
-    const int b = a.list ? a.list[pos] : pos;
+    int chain;
+    const int b = schur_locate(a, blockIdx.z, chain);
+    if (b < 0) return;
     const int S = a.S, ldm = btd_ldm(S), lds = btd_lds(S);
+    const int ar = a.r[chain], arp = a.rprev[chain];
     double *Jb = a.J + (size_t)b * a.j_stride;
-    double *Mr = Jb + (size_t)a.r * btd_row_doubles(S);
-    const double *A = Mr + (size_t)S * ldm;                                             // L_r
-    const double *Bm = Jb + (size_t)(a.r - 1) * btd_row_doubles(S) + (size_t)S * ldm;   // U'_{r-1}
+    double *Mr = Jb + (size_t)ar * btd_row_doubles(S);
+    const bool inm = a.a_in_m[chain] != 0;
+    const double *A = inm ? Mr + gjp_npc(S) : Mr + (size_t)S * ldm;                    // coupling block of row r
+    const int lda = inm ? ldm : lds;
+    const double *Bm = Jb + (size_t)arp * btd_row_doubles(S) + (size_t)S * ldm;         // X'_prev
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = blockIdx.y * kSchurBM;
     const int ntx = (S + kSchurBN - 1) / kSchurBN;
     if ((int)blockIdx.x == ntx) {
         // right-hand side: rhs_r[row] -= sum_k A[row][k] b'_{r-1}[k], one warp per row
-        const double *x = a.rhs + (size_t)b * a.rhs_stride + (size_t)(a.r - 1) * S;
+        const double *x = a.rhs + (size_t)b * a.rhs_stride + (size_t)arp * S;
         for (int rr = warp; rr < kSchurBM; rr += 8) {
             const int row = r0 + rr;
             if (row >= S) break;
-            const double *ar = A + (size_t)row * lds;
+            const double *arow = A + (size_t)row * lda;
             double acc = 0.;
-            for (int k = lane; k < S; k += 32) acc = fma(ar[k], x[k], acc);
+            for (int k = lane; k < S; k += 32) acc = fma(arow[k], x[k], acc);
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
             if (lane == 0) Mr[(size_t)row * ldm + gjp_npc(S) + S] -= acc;
         }
@@ -474,8 +524,8 @@ __global__ void __launch_bounds__(256) k_btd_schur(SchurArgs a) {
         for (int i = 0; i < 2; ++i) {
             const int ch = tid + 256 * i;
             const int rr = ch >> 3, kc = (ch & 7) * 2;
-            const bool ok = r0 + rr < S && k0 + kc < lds;
-            cp_async16(&As[buf][rr][kc], A + (size_t)(ok ? r0 + rr : 0) * lds + (ok ? k0 + kc : 0), ok);
+            const bool ok = r0 + rr < S && k0 + kc < lds;  // (a chunk may reach one column past S: times a zero-filled row of B)
+            cp_async16(&As[buf][rr][kc], A + (size_t)(ok ? r0 + rr : 0) * lda + (ok ? k0 + kc : 0), ok);
         }
         // B tile: 16 k x 64 columns: 32 chunks per row
 #pragma unroll
@@ -533,15 +583,16 @@ __global__ void __launch_bounds__(256) k_btd_schur(SchurArgs a) {
     }
 }
 
-// back substitution of the block-Thomas chain: x_r = b'_r - U'_r x_{r+1}, in place in rhs.  grid (row chunks, circuits)
+// back substitution of the block-Thomas chains: x_r = b'_r - X'_r x_q, q = rprev (the neighbour nearer the middle), in place
+// in rhs.  grid (row chunks, circuits x chains)
 __global__ void __launch_bounds__(256) k_btd_back(SchurArgs a) {
-    const int pos = blockIdx.y;
-    if (a.count && pos >= *a.count) return;
-    const int b = a.list ? a.list[pos] : pos;
+    int chain;
+    const int b = schur_locate(a, blockIdx.y, chain);
+    if (b < 0) return;
     const int S = a.S, ldm = btd_ldm(S), lds = btd_lds(S);
-    const double *U = a.J + (size_t)b * a.j_stride + (size_t)a.r * btd_row_doubles(S) + (size_t)S * ldm;  // U'_r
-    double *x = a.rhs + (size_t)b * a.rhs_stride + (size_t)a.r * S;
-    const double *xn = x + S;
+    const double *U = a.J + (size_t)b * a.j_stride + (size_t)a.r[chain] * btd_row_doubles(S) + (size_t)S * ldm;  // X'_r
+    double *x = a.rhs + (size_t)b * a.rhs_stride + (size_t)a.r[chain] * S;
+    const double *xn = a.rhs + (size_t)b * a.rhs_stride + (size_t)a.rprev[chain] * S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int row = blockIdx.x * 8 + warp; row < S; row += gridDim.x * 8) {
         const double *ur = U + (size_t)row * lds;
