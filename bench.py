@@ -12,7 +12,7 @@ with the PNP extension instead.
     python bench.py --scaling strong ...                           (the ONE 4096-point sweep split over the ranks)
     python bench.py --impl reference ...                           (CPU arm: the oracle port on all host cores)
 
---scaling weak (default): 64 x 64 points PER GPU -- a (64 N) x 64 grid whose points are dealt round-robin to the ranks.
+--scaling weak (default): 64 x 64 points PER GPU -- a 64 x (64 N) (vbias x vin) grid whose points are dealt round-robin to the ranks.
 value  : solves/s with the parameter arrays resident in HBM (DeviceBatch.solve: DC + ladder + Newton on device,
          results packed and gathered with one NCCL all_gather_into_tensor for N > 1)
 e2e    : solves/s through hb.run_sweep() (hb.distributed = True for N > 1): host arrays in, host arrays out
@@ -42,14 +42,16 @@ import numpy as np  # noqa: E402
 GRID = 64
 
 
-def grid_points(nrows, workload):
-    """(vbias, vin) of a nrows x 64 grid, flattened vbias-major"""
+def grid_points(ncols, workload):
+    """(vbias, vin) of a 64 x ncols grid (64 bias points, ncols amplitudes over the same range), flattened vbias-major.
+    Weak scaling refines the AMPLITUDE axis (ncols = 64 N): dealt round-robin, every rank then holds what one GPU holds at
+    N = 1 -- all 64 bias points with 64 amplitudes each -- instead of 64 N bias points with 8 amplitudes each."""
     if workload == 'activeload':
-        vb = np.linspace(1.3, 1.7, nrows)
-        vin = np.linspace(20e-6, 1e-3, GRID)
+        vb = np.linspace(1.3, 1.7, GRID)
+        vin = np.linspace(20e-6, 1e-3, ncols)
     else:
-        vb = np.linspace(1.0, 1.4, nrows)
-        vin = np.linspace(100e-6, 50e-3, GRID)
+        vb = np.linspace(1.0, 1.4, GRID)
+        vin = np.linspace(100e-6, 50e-3, ncols)
     VB, VIN = np.meshgrid(vb, vin, indexing='ij')
     return VB.ravel(), VIN.ravel()
 
@@ -363,6 +365,7 @@ def run_gpu(args):
 
     # ---- end to end: the call a user makes, host arrays in / out (sharded over the ranks for N > 1)
     hb.distributed = world > 1
+    hb.gather_root = 0 if world > 1 else None   # the gathered results are read back to the host on rank 0 only
     hb.report_levels = False   # the 768 B per circuit of per-level reports are optional output; parity fetches them below
     sw_all = sweeps_of(VB_all, VIN_all)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -379,9 +382,11 @@ def run_gpu(args):
     e2e = Btot * args.steps / float(tt.item())
     per_circuit_in = sum(getattr(pb, n).nbytes for n in ('tones', 'lin_val', 'src_val', 'diode_par', 'bjt_par', 'cubic_par')) // B
     h2d = int(per_circuit_in * B)                      # this rank's parameter upload
-    per_circuit_out = (res.V.nbytes + res.Vf.nbytes + res.converged.nbytes + res.newton_iters.nbytes +
-                       res.lu_count.nbytes + res.err.nbytes) // Btot
-    d2h = int(per_circuit_out * (Btot if world > 1 else B))   # N > 1: every rank reads the gathered results of the whole job
+    d2h = 0
+    if rank == 0:
+        per_circuit_out = (res.V.nbytes + res.Vf.nbytes + res.converged.nbytes + res.newton_iters.nbytes +
+                           res.lu_count.nbytes + res.err.nbytes) // Btot
+        d2h = int(per_circuit_out * Btot)   # N > 1: rank 0 reads the gathered results of the whole job
 
     # ---- parity on a seeded random sample of the grid (outside the timed region) + CPU baseline beside it
     parity = cpu = None
@@ -396,6 +401,7 @@ def run_gpu(args):
         parity = parity_report(gres.V, gres.level_iters, gres.converged, np.arange(len(idx)), out)
         # and the big batch's own phasors at the same points (same circuits, another batch: must agree to rounding)
         parity['batch_vs_sample_rel'] = float(np.max(np.abs(res.V[idx] - gres.V)) / np.max(np.abs(gres.V)))
+        hb.gather_root = None
         if world == 1 and not args.no_cpu:
             cpu = {'value': v, 'unit': 'solves/s', 'cores': cores, 'kind': 'port',
                    'sample': '%d of the 4096 grid points (default_rng(0) subset), cold start each, %d worker processes, '
@@ -461,7 +467,8 @@ def run_gpu(args):
             'converged': '%d/%d' % (nconv, Btot), 'newton_iters_per_solve': newton_all / Btot, 'lu_per_solve': lus_all / Btot,
             'e2e': {'value': e2e, 'unit': 'solves/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'path': 'hb.run_sweep (hb.distributed=%s, report_levels=False): pinned host arrays -> H2D -> DC + solve '
-                            '-> %sD2H' % (world > 1, 'pack + NCCL all_gather_into_tensor -> ' if world > 1 else '')},
+                            '-> %sD2H%s' % (world > 1, 'pack + NCCL all_gather_into_tensor -> ' if world > 1 else '',
+                                         ' of the whole job\'s results on rank 0 (hb.gather_root = 0)' if world > 1 else '')},
             'gpu_launches': launches, 'kernels': {k: {'launches': n, 'ms': round(m, 3)} for k, (n, m) in prof.items() if n},
             'roofline': roof, 'roofline_device_eval': devroof, 'parity': parity, 'per_rank': per_rank,
             'cpu_baseline': cpu, 'clocks': clocks,

@@ -55,6 +55,12 @@ def _worker(rank, world, port, B, out):
     pb.set(h['i2'], 'ac', np.linspace(1e-3, 2e-3, B))
     res = _dist.run_block_distributed(FakePlan, pb, {}, None, run_fn=_fake_run)
     idx = _dist.shard_indices(B, rank, world)
+    # the form hb.run_sweep uses: the block already holds this rank's circuits only; results on rank 0 only
+    res2 = _dist.run_block_distributed(FakePlan, _dist.slice_block(pb, idx), {}, None, run_fn=_fake_run, root=0, total=B)
+    if rank == 0:
+        assert np.array_equal(res2.V, res.V) and np.array_equal(res2.Vf, res.Vf) and np.array_equal(res2.err, res.err)
+    else:
+        assert res2 is None
     if rank == 0:
         np.savez(out, V=res.V, Vf=res.Vf, it=res.newton_iters, conv=res.converged, err=res.err, lev=res.level_iters,
                  alpha=res.level_alpha, lu=res.lu_count)

@@ -37,6 +37,8 @@ class MultiToneHarmonicBalance:
         self.block_sparse = None      # fused engine: None = block-sparse LU over node blocks when the core's block
                                       # structure is sparse, True / False = whenever it applies / never (dense solve)
         self.distributed = False      # run_batch / run_sweep: shard the circuits over torch.distributed ranks, gather
+        self.gather_root = None       # distributed: None = every rank gets the whole batch's results; r = only rank r
+                                      # (the other ranks' run_batch / run_sweep return None)
         self.report_levels = True     # run_batch / run_sweep: copy the per-level reports back (768 B per circuit)
         self.last = None              # BatchResult of the last call
 
@@ -135,6 +137,16 @@ class MultiToneHarmonicBalance:
         swept explicitly."""
         plan, topo = self._setup(netlist)
         B = len(np.asarray(sweeps[0][2])) if sweeps else len(np.asarray(freq))
+        total = None
+        if self.distributed:
+            # build the parameter block of THIS rank's circuits only (b % world == rank)
+            import torch.distributed as dist
+            from .._dist import shard_indices
+            idx = shard_indices(B, dist.get_rank(), dist.get_world_size())
+            sweeps = [(dev, field, np.asarray(values, dtype=np.float64)[idx]) for dev, field, values in sweeps]
+            if freq is not None:
+                freq = np.asarray(freq, dtype=np.float64)[idx]
+            total, B = B, len(idx)
         pb = ParamBlock(topo, self.freq, B)
         for dev, field, values in sweeps:
             pb.set(dev, field, values)
@@ -148,13 +160,17 @@ class MultiToneHarmonicBalance:
                     if dev.freq == f_nom:  # the filter's exact-equality test (IdealHarmonicFilter.py:34) must keep hitting
                         pb.set(dev, 'freq', col)
             pb.set_tones(*cols)
-        return self._run_block(plan, pb, V0)
+        return self._run_block(plan, pb, V0, total)
 
-    def _run_block(self, plan, pb, V0):
+    def _run_block(self, plan, pb, V0, total=None):
         self._had_v0 = V0 is not None
         if self.distributed:
             from .._dist import run_block_distributed
-            res = run_block_distributed(plan, pb, self.options, V0, levels=self.report_levels)
+            res = run_block_distributed(plan, pb, self.options, V0, levels=self.report_levels, root=self.gather_root,
+                                        total=total)
+            if res is None:
+                self.last = None
+                return None
         else:
             res = E.run_host(plan, pb, self.options, V0, want_levels=self.report_levels)
         res.freqs = self._freqs(plan)

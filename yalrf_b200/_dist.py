@@ -109,7 +109,7 @@ def gather_packed(local, B, group=None):
     return rows[b % world, b // world]     # circuit b = row b // world of rank b % world
 
 
-def gather_unpack_device(plan, local, B, lay, group=None):
+def gather_unpack_device(plan, local, B, lay, group=None, root=None):
     """NCCL path: local = this rank's [n][R] rows in HBM.  ONE all_gather_into_tensor, the rows put into circuit order
     by one device copy (circuit b = row b // world of rank b % world: a transpose of the [world][nmax] row grid), every
     field split off on the device and copied straight into the page-locked arrays of the BatchResult -- no host-side
@@ -124,6 +124,8 @@ def gather_unpack_device(plan, local, B, lay, group=None):
         t = torch.cat([t, torch.zeros((nmax - t.shape[0], R), dtype=t.dtype, device=t.device)])
     out = torch.empty((world * nmax, R), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    if root is not None and dist.get_rank(group) != root:
+        return None                                  # only the root reads the gathered results back to the host
     rows = out.view(world, nmax, R).transpose(0, 1).reshape(world * nmax, R)[:B]      # circuit order
     full = BatchResult(plan, B, pinned=True, levels=lay.levels)
     keep = []
@@ -141,22 +143,27 @@ def gather_unpack_device(plan, local, B, lay, group=None):
     return full
 
 
-def run_block_distributed(plan, pb, options, V0=None, group=None, run_fn=None, levels=True):
+def run_block_distributed(plan, pb, options, V0=None, group=None, run_fn=None, levels=True, root=None, total=None):
     """Solve this rank's circuits of the block and gather.  run_fn(plan, pb, options, V0) -> BatchResult (host) is
-    for tests; the default keeps parameters and results in HBM (DeviceBatch) and packs / gathers on the device."""
+    for tests; the default keeps parameters and results in HBM (DeviceBatch) and packs / gathers on the device.
+    root: None = every rank returns the whole batch's results; a rank number = only that rank does (the others return
+    None and skip the device-to-host copy of the gathered rows).  total: pb already holds only THIS rank's circuits
+    (shard_indices(total, rank, world)) of a batch of `total` circuits."""
     import torch.distributed as dist
     from . import _engine as E
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    idx = shard_indices(pb.B, rank, world)
+    B = pb.B if total is None else total
+    idx = shard_indices(B, rank, world)
     lay = PackLayout(plan, levels)
-    v0 = None if V0 is None else np.asarray(V0, dtype=np.float64).reshape(pb.B, -1)[idx]
+    v0 = None if V0 is None else np.asarray(V0, dtype=np.float64).reshape(B, -1)[idx]
+    mine = (lambda: pb) if total is not None else (lambda: slice_block(pb, idx))
     if len(idx) == 0:
         local = np.zeros((0, lay.R))
     elif run_fn is not None:
-        local = pack_host(run_fn(plan, slice_block(pb, idx), options, v0), lay)
+        local = pack_host(run_fn(plan, mine(), options, v0), lay)
     else:
         import torch
-        db = E.DeviceBatch(plan, slice_block(pb, idx), pinned_upload=True)
+        db = E.DeviceBatch(plan, mine(), pinned_upload=True)
         if v0 is not None:
             db.V.copy_(torch.from_numpy(v0), non_blocking=False)
         db.solve(options, have_v0=v0 is not None)
@@ -166,5 +173,8 @@ def run_block_distributed(plan, pb, options, V0=None, group=None, run_fn=None, l
             db.solve(options, have_v0=True, with_dc=True)
         local = pack_device(db, lay)
         if dist.get_backend(group) == 'nccl':
-            return gather_unpack_device(plan, local, pb.B, lay, group)
-    return unpack(plan, gather_packed(local, pb.B, group), lay)
+            return gather_unpack_device(plan, local, B, lay, group, root)
+    rows = gather_packed(local, B, group)
+    if root is not None and rank != root:
+        return None
+    return unpack(plan, rows, lay)
