@@ -125,16 +125,48 @@ def extra_fixtures(Netlist, MTHB, save):
          F3=rec.F[3])
 
 
+# the oscillation point the GPU engine's 2 x 2 Newton iteration finds for the Peltz oscillator (deterministic; the test
+# checks that the engine still lands there before it uses the fixture)
+PELTZ_GPU_ROOT = (71092.6637049824, 0.7501097624413049)
+
+
+def osc_root_fixture(Netlist, MTHB, save):
+    """the REFERENCE's oscillator objective evaluated at the GPU engine's answer.  The reference's own HB
+    solves the Peltz oscillator with its probe fixed at the GPU root (cold start, like the first objective evaluation
+    of run_oscillator, :171), and Yosc is formed exactly as objFunc does (:183-186).
+        python tests/golden/make_golden.py --osc-root"""
+    import circuits
+    f, v = PELTZ_GPU_ROOT
+    y = Netlist('Oscillator')
+    h = circuits.peltz(y)
+    circuits.add_probe(y, 'HB1', h['node'], f, v)
+    hb = MTHB('HB1', f, h['K'])
+    (conv, freqs, Vf, _, _), text = quiet_run(hb.run, y)
+    al, its, errs = parse_levels(text)
+    n1 = hb.get_node_idx(h['node'])
+    n2 = hb.get_node_idx('HB1.nosc2')
+    Iosc = (Vf[n1, 1] - Vf[n2, 1]) * 1e9           # Zoscprobe.g (IdealHarmonicFilter.py:12)
+    Yosc = Iosc / Vf[n1, 1]
+    save('peltz_ref_at_gpu_root', converged=conv, fosc=f, Vosc=v, freqs=freqs, Vf=Vf, V=hb.V, iters=its, yosc=Yosc,
+         ulp_floor=1e9 * np.spacing(abs(Vf[n1, 1])) / abs(Vf[n1, 1]))
+    print('reference |Yosc| at the GPU root: %.3e S (one ulp of the probe voltage = %.3e S)' % (
+        abs(Yosc), 1e9 * np.spacing(abs(Vf[n1, 1])) / abs(Vf[n1, 1])))
+
+
+def save_npz(name, **arrs):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **arrs)
+    print('wrote', path, {k: np.asarray(v).shape for k, v in arrs.items()})
+
+
 def main():
     import circuits
     Netlist, MTHB = import_reference()
     out = {}
+    if '--osc-root' in sys.argv:
+        return osc_root_fixture(Netlist, MTHB, save_npz)
 
-    def save(name, **arrs):
-        path = os.path.join(HERE, name + '.npz')
-        np.savez_compressed(path, **arrs)
-        print('wrote', path, {k: np.asarray(v).shape for k, v in arrs.items()})
-
+    save = save_npz
     if '--extra' in sys.argv:
         return extra_fixtures(Netlist, MTHB, save)
     if '--ladder' in sys.argv:   # config 5 reductions (SURVEY 8d): minutes of reference time

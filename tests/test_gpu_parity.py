@@ -404,6 +404,40 @@ def test_vanderpol_newton(yb, golden):
     assert abs(r.fosc[1] - r.fosc[0]) / r.fosc[0] < 1e-9
 
 
+def test_oscillator_root_under_reference_objective(yb, golden):
+    """the GPU engine's oscillation point fed back through the REFERENCE.  tests/golden/
+    peltz_ref_at_gpu_root.npz (make_golden.py --osc-root) holds the unmodified reference's HB solution of the Peltz
+    oscillator with its probe fixed at the GPU root and the reference's own objective Yosc (:183-186) there: the
+    objective sits below its own resolution (one ulp of the probe voltage x 1e9 S), and the reference's phasors at that
+    point are the GPU's."""
+    g = golden('peltz_ref_at_gpu_root')
+    assert bool(g['converged'])
+    assert abs(complex(g['yosc'])) < float(g['ulp_floor'])                   # 8.1e-10 S against 1.5e-7 S
+    y = yb.Netlist('Oscillator')
+    h = circuits.peltz(y)
+    hb = mthb('HB1')
+    conv, freqs, Vf, _, _ = hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node'])
+    assert conv
+    # the engine still lands on the point the fixture was written for
+    assert abs(hb.fosc - float(g['fosc'])) / float(g['fosc']) < 1e-10
+    assert abs(hb.Vosc - float(g['Vosc'])) / float(g['Vosc']) < 1e-10
+    # the same solve as the fixture's -- cold start, probe fixed at the root -- on the GPU: identical iteration counts,
+    # phasors within 1e-9 (the oscillator run's own last iterate is a warm start: another end of the iteration)
+    y2 = yb.Netlist('Oscillator')
+    circuits.peltz(y2)
+    circuits.add_probe(y2, 'HB1', h['node'], float(g['fosc']), float(g['Vosc']))
+    hb2 = mthb('HB1', float(g['fosc']), h['K'])
+    assert hb2.run(y2)[0]
+    assert hb2.last.levels() == g['iters'].tolist()
+    V, G = hb2.V.reshape(hb2.N, hb2.S), g['V'].reshape(hb2.N, hb2.S)
+    probe = hb2.get_node_idx('HB1.nosc1')
+    for n in range(hb2.N):
+        if n != probe:
+            assert np.max(np.abs(V[n] - G[n])) < 1e-9 * np.max(np.abs(G)), n
+    # the probe-current node carries 1e9 S x rounding noise in the reference (see test_peltz_probe_fixed)
+    assert np.max(np.abs(V[probe] - G[probe])) < 1e9 * 8 * np.spacing(0.75)
+
+
 def test_peltz_oscillator_fmin_replay(yb, golden):
     """hb.osc_method = 'fmin': the reference's own Nelder-Mead outer loop (:204-212), every evaluation a GPU solve."""
     g = golden('peltz_osc')

@@ -158,6 +158,22 @@ def test_peltz_probe_fixed(golden):
     assert relmax(hb.V, g['V']) < 1e-9
 
 
+def test_peltz_at_gpu_root(golden):
+    """the oracle against the reference at the oscillation point the GPU engine finds (make_golden.py --osc-root)"""
+    g = golden('peltz_ref_at_gpu_root')
+    y = ho.FlatNetlist()
+    h = circuits.peltz(y)
+    circuits.add_probe(y, 'HB1', h['node'], float(g['fosc']), float(g['Vosc']))
+    hb = ho.HBOracle('HB1', float(g['fosc']), h['K'])
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv and bool(g['converged'])
+    assert levels(hb) == g['iters'].tolist()
+    V, G = hb.V.reshape(-1, 21), g['V'].reshape(-1, 21)
+    probe = y.get_node_idx('HB1.nosc1') - 1
+    keep = [n for n in range(V.shape[0]) if n != probe]          # the probe-current node: 1e9 S x rounding noise
+    assert relmax(V[keep], G[keep]) < 1e-9
+
+
 def test_peltz_oscillator(golden):
     g = golden('peltz_osc')
     y = ho.FlatNetlist()
