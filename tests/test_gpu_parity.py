@@ -4,6 +4,7 @@ reference (tests/golden/) and against the numpy oracle on the same inputs.  Run 
 Tolerances: 1e-9 relative on converged phasors (BASELINE.json north_star); per-level Newton iteration
 counts must be identical."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -919,3 +920,41 @@ def test_convert_to_time_and_two_tone_reconstruction(yb, golden):
                               for i in range(1, len(freqs)))
         assert np.max(np.abs(row - ref)) < 1e-12 * np.max(np.abs(ref))
     assert hb2.to_time('n2', tt).shape == (500,)
+
+
+# ----------------------------------------------------------------------------- cold solve: DC groups / DC beside HB
+_COLD_SCRIPT = r'''
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + '/tests')
+import circuits, yalrf_b200
+from yalrf_b200.Analyses import MultiToneHarmonicBalance
+y = yalrf_b200.YalRF('Differential Amplifier')
+h = circuits.diffamp(y)
+vb = np.repeat(np.linspace(1.0, 1.4, 12), 8)
+vb[8] = np.nextafter(vb[8], 2.0)          # one ulp away from its neighbours: must NOT share their DC analysis
+vin = np.tile(np.linspace(100e-6, 50e-3, 8), 12)
+hb = MultiToneHarmonicBalance('HB1', h['freq'], h['K'])
+r = hb.run_sweep(y, [(h['i2'], 'ac', vin / 2), (h['i4'], 'ac', vin / 2), (h['i3'], 'dc', vb), (h['i5'], 'dc', vb)])
+np.savez(sys.argv[2], V=r.V, conv=r.converged, it=r.newton_iters, lev=r.level_iters)
+'''
+
+
+def test_cold_solve_modes_bit_identical(tmp_path):
+    """The cold solve's three ways of getting the operating points -- one DC analysis per group of circuits with
+    bit-identical DC inputs, run beside the HB kernel (default); the same in front of it (YHB_NO_DC_OVERLAP); one DC
+    analysis per circuit in front of it (+ YHB_NO_DC_GROUPS) -- give bit-identical results: 96 DiffAmp points on 12
+    bias values, one of them moved by one ulp (it must form a group of its own)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for i, env in enumerate(({}, {'YHB_NO_DC_OVERLAP': '1'}, {'YHB_NO_DC_OVERLAP': '1', 'YHB_NO_DC_GROUPS': '1'})):
+        out = str(tmp_path / ('m%d.npz' % i))
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, '-c', _COLD_SCRIPT, root, out], check=True, env=e, timeout=300)
+        outs.append(np.load(out))
+    assert int((outs[0]['conv'] > 0).sum()) == 96
+    for o in outs[1:]:
+        for k in ('V', 'conv', 'it', 'lev'):
+            np.testing.assert_array_equal(o[k], outs[0][k])
