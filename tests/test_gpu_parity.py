@@ -958,3 +958,35 @@ def test_cold_solve_modes_bit_identical(tmp_path):
     for o in outs[1:]:
         for k in ('V', 'conv', 'it', 'lev'):
             np.testing.assert_array_equal(o[k], outs[0][k])
+
+
+def test_linear_only_netlist_vs_oracle(yb):
+    """Edge case: a netlist without any nonlinear device (R, C, L behind a gyrator source): hb_loop still runs its minimum
+    of three iterations (:596) on a Jacobian that is the linear admittance alone; the DC analysis takes the linear branch
+    (DC.py:90-95).  Single solve and a three-point amplitude sweep against the oracle."""
+    from oracle import hb_oracle as ho
+
+    def build(y, ac=2.0):
+        i1 = y.add_iac('I1', 'nx', 'gnd', ac=ac, freq=1e6)
+        y.add_gyrator('G1', 'nx', 'n1', 'gnd', 'gnd', 1)
+        y.add_resistor('R1', 'n1', 'n2', 50)
+        y.add_capacitor('C1', 'n2', 'gnd', 2e-9)
+        y.add_inductor('L1', 'n2', 'n3', 1e-6)
+        y.add_resistor('R2', 'n3', 'gnd', 75)
+        return i1
+
+    y = yb.Netlist('linear')
+    i1 = build(y)
+    hb = mthb('HB1', 1e6, 4)
+    conv, freqs, Vf, _, _ = hb.run(y)
+    yo = ho.FlatNetlist()
+    build(yo)
+    o = ho.HBOracle('HB1', 1e6, 4)
+    conv_o = o.run(yo)[0]
+    assert conv and conv_o
+    assert hb.last.levels() == [l[1] for l in o.level_log]
+    assert relmax(hb.V, o.V) < 1e-9
+    res = hb.run_sweep(y, [(i1, 'ac', np.array([0.5, 1.0, 2.0]))])
+    assert res.converged.tolist() == [1, 1, 1]
+    assert relmax(res.V[2], o.V[:, 0]) < 1e-9
+    assert relmax(res.V[0] * 4.0, res.V[2]) < 1e-12          # linear circuit: the response scales with the drive
