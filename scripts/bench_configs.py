@@ -38,4 +38,13 @@ t = time.perf_counter(); hb.run_oscillator(y, h['f0'], h['K'], h['V0'], h['node'
 res['cfg2_outer_iterations'] = int(hb.last_osc.outer_iterations[0]); res['cfg2_fosc'] = hb.fosc; res['cfg2_Vosc'] = hb.Vosc; res['cfg2_yosc'] = hb.osc_yosc
 f0 = np.linspace(70e3, 90e3, 64); V0 = np.linspace(0.05, 0.8, 64)
 dt, r = timeit(lambda: hb.run_oscillator_batch(y, f0, h['K'], V0, h['node']), reps=2); res['cfg2_batch64_oscillators_per_s'] = 64 / dt; res['cfg2_batch64_converged'] = int(r.converged.sum())
+# config 2, the reference's heaviest oscillator workload: the Colpitts divider-ratio sweep of tests/HBOscillators.ipynb cell 8
+# (20 run_oscillator calls, K = 20, 110 s in the reference) as one batched call
+y = yalrf_b200.Netlist('o2'); h = circuits.colpitts_nvec(y)
+hb = MultiToneHarmonicBalance('HB1'); hb.options['maxiter'] = 100
+nvec = np.geomspace(0.05, 0.6, 20)
+sw = [(h['c1'], 'C', h['ct'] / (1 - nvec)), (h['c2'], 'C', h['ct'] / nvec)]
+dt, r = timeit(lambda: hb.run_oscillator_batch(y, np.full(20, h['f0']), h['K'], h['V0'](nvec), h['node'], sweeps=sw, maxiter=60), reps=2)
+res['cfg2_colpitts_nvec20_s'] = dt; res['cfg2_colpitts_nvec20_converged'] = int(r.converged.sum())
+res['cfg2_colpitts_nvec20_outer_iterations_max'] = int(r.outer_iterations.max()); res['cfg2_colpitts_nvec20_yosc_max'] = float(np.max(r.yosc))
 print(json.dumps(res, indent=1))

@@ -246,6 +246,27 @@ def colpitts_cb(y):
     return dict(q1=q1, f0=9e6, V0=1, K=20, node='nc')
 
 
+def colpitts_nvec(y, n=0.3):
+    """tests/HBOscillators.ipynb cell 8 ('Oscillator Parameter Sweep'): Colpitts oscillator whose capacitive divider ratio n
+    the notebook sweeps over np.geomspace(0.05, 0.6, 20) in a loop around run_oscillator (its heaviest workload)."""
+    vcc, vbias, ibias, rl, fosc, l = 5, 1, 1e-3, 850, 50e6, 50e-9
+    ct = 1 / (l * (2 * np.pi * fosc) ** 2)
+    y.add_idc('I1', 'nx1', 'gnd', dc=vcc)
+    y.add_gyrator('G1', 'nx1', 'nvcc', 'gnd', 'gnd', 1)
+    y.add_idc('I2', 'ny1', 'gnd', dc=vbias)
+    y.add_gyrator('G2', 'ny1', 'nb', 'gnd', 'gnd', 1)
+    y.add_idc('I3', 'gnd', 'ne', dc=ibias)
+    y.add_resistor('Rl', 'nvcc', 'nc', rl)
+    y.add_inductor('L1', 'nvcc', 'nc', l)
+    c1 = y.add_capacitor('C1', 'nc', 'ne', ct / (1 - n))
+    c2 = y.add_capacitor('C2', 'ne', 'gnd', ct / n)
+    q1 = y.add_bjt('Q1', 'nb', 'nc', 'ne')
+    q1.options['Is'] = 1e-15
+    q1.options['Bf'] = 100
+    return dict(q1=q1, c1=c1, c2=c2, ct=ct, f0=1 / (2 * np.pi * np.sqrt(l * ct)), V0=lambda n_: 2 * ibias * rl * (1 - n_),
+                K=20, node='nc', rl=rl, ibias=ibias)
+
+
 def add_probe(y, name, node, f, amp):
     """The oscillator probe of run_oscillator (MultiToneHarmonicBalance.py:146-150) at a fixed (f, amplitude)."""
     y.add_iac(name + '.I.Oscprobe', name + '.nosc1', 'gnd', ac=amp, freq=f)

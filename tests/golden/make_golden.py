@@ -159,12 +159,37 @@ def save_npz(name, **arrs):
     print('wrote', path, {k: np.asarray(v).shape for k, v in arrs.items()})
 
 
+def colpitts_nvec_fixture(Netlist, MTHB, save):
+    """tests/HBOscillators.ipynb cell 8: the 'single iteration' run_oscillator of the Colpitts divider-ratio sweep (n = 0.3)
+    and two more points of its nvec loop, each a cold run_oscillator of the unmodified reference.
+        python tests/golden/make_golden.py --colpitts-nvec"""
+    import circuits
+    nvec = np.array([0.05, 0.3, 0.6])
+    fosc, vosc, vtank, Vfs = [], [], [], []
+    for n in nvec:
+        y = Netlist('Oscillator Parameter Sweep')
+        h = circuits.colpitts_nvec(y, n=float(n))
+        hb = MTHB('HB1')
+        hb.options['maxiter'] = 100
+        (res, text) = quiet_run(hb.run_oscillator, y, h['f0'], h['K'], h['V0'](float(n)), h['node'])
+        conv, freqs, Vf, _, _ = res
+        assert conv
+        fosc.append(float(re.findall(r'Frequency of oscillation = (\S+) Hz', text)[-1]))
+        vosc.append(float(re.findall(r'Oscillation amplitude = (\S+) V', text)[-1]))
+        vtank.append(abs(Vf[hb.get_node_idx('nc'), 1]))
+        Vfs.append(Vf)
+        print(n, fosc[-1], vosc[-1], vtank[-1])
+    save('colpitts_nvec', nvec=nvec, fosc=np.array(fosc), Vosc=np.array(vosc), vtank=np.array(vtank), Vf=np.array(Vfs))
+
+
 def main():
     import circuits
     Netlist, MTHB = import_reference()
     out = {}
     if '--osc-root' in sys.argv:
         return osc_root_fixture(Netlist, MTHB, save_npz)
+    if '--colpitts-nvec' in sys.argv:
+        return colpitts_nvec_fixture(Netlist, MTHB, save_npz)
 
     save = save_npz
     if '--extra' in sys.argv:

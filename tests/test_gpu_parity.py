@@ -492,6 +492,50 @@ def test_oscillator_sweep_vs_oracle(yb):
         assert relmax(r.V[k], o.V[:, 0]) < 1e-6, k      # same circuit, same probe: the HB solutions agree
 
 
+def test_colpitts_divider_sweep(yb, golden):
+    """tests/HBOscillators.ipynb cell 8 (the reference's heaviest workload: a loop of 20 run_oscillator calls over the
+    capacitive divider ratio n of a Colpitts oscillator, K = 20, 110 s there) as ONE batched device call.  Three of its
+    points against cold run_oscillator runs of the unmodified reference (colpitts_nvec.npz; its Nelder-Mead stops at 300
+    evaluations, so its answer is good to ~1e-4 in Vosc), and every point against the oracle: with the probe fixed at the
+    GPU's (fosc, Vosc) the oracle's own HB solution carries no probe current, and its phasors are the GPU's."""
+    from oracle import hb_oracle as ho
+    from yalrf_b200 import _osc
+    from yalrf_b200._flatten import ParamBlock, Topology
+    g = golden('colpitts_nvec')
+    nvec = g['nvec']
+    y = yb.Netlist('Oscillator Parameter Sweep')
+    h = circuits.colpitts_nvec(y)
+    hb = mthb('HB1')
+    hb.options['maxiter'] = 100
+    sweeps = [(h['c1'], 'C', h['ct'] / (1 - nvec)), (h['c2'], 'C', h['ct'] / nvec)]
+    r = hb.run_oscillator_batch(y, np.full(len(nvec), h['f0']), h['K'], h['V0'](nvec), h['node'], sweeps=sweeps, maxiter=60)
+    assert r.converged.all(), (r.converged, r.yosc)
+    assert np.max(r.yosc) < 1e-12 and np.all(r.outer_iterations <= 10)
+    assert np.max(np.abs(r.fosc / g['fosc'] - 1)) < 1e-5
+    assert np.max(np.abs(r.Vosc / g['Vosc'] - 1)) < 1e-3
+    nc = r.netlist.get_node_idx('nc')
+    assert np.max(np.abs(np.abs(r.Vf[:, nc - 1, 1]) / g['vtank'] - 1)) < 1e-3
+    S = 2 * h['K'] + 1
+    for k in range(len(nvec)):
+        yo = ho.FlatNetlist()
+        circuits.colpitts_nvec(yo, n=float(nvec[k]))
+        circuits.add_probe(yo, 'HB1', 'nc', float(r.fosc[k]), float(r.Vosc[k]))
+        o = ho.HBOracle('HB1', float(r.fosc[k]), h['K'])
+        o.options['maxiter'] = 100
+        assert o.run(yo)[0]
+        for _ in range(3):
+            assert o.run(yo, o.V)[0]
+        topo = Topology(r.netlist, 1, (h['K'],))
+        pb = ParamBlock(topo, float(r.fosc[k]), 1)
+        pb.set(h['c1'], 'C', [float(h['ct'] / (1 - nvec[k]))])
+        pb.set(h['c2'], 'C', [float(h['ct'] / nvec[k])])
+        pb.finalize()
+        pz = [d for _, _, d in topo.lin if d.name == 'HB1IHF.Oscprobe'][0]
+        Y = _osc.kcl_yosc(topo, pb, pz, nc, o.V.reshape(1, -1), o.last_Inl.reshape(1, -1), S)
+        assert abs(Y[0]) < 1e-8, (k, abs(Y[0]))
+        assert relmax(r.V[k], o.V[:, 0]) < 1e-6, k
+
+
 # ----------------------------------------------------------------------------- fused engine: block-sparse core LU
 @pytest.mark.parametrize('mode', [None, True, False])
 def test_block_sparse_core_lu(yb, golden, mode):
