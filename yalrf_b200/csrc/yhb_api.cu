@@ -1490,6 +1490,7 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
             }
             ws.dc_wait = 1;
             YHB_CUDA(cudaMemsetAsync(ws.dc_ready, 0, sizeof(int) * ((size_t)B + 8), st));
+            YHB_CUDA(cudaMemsetAsync(ws.list[0], 0, sizeof(int) * (size_t)B, st));  // the HB kernel's deferred list
         }
         leader = dc_groups(pl, p, L, st, overlap);  // before the fork: the HB kernel reads the leaders too
     }
