@@ -1004,6 +1004,24 @@ def test_cold_solve_modes_bit_identical(tmp_path):
             np.testing.assert_array_equal(o[k], outs[0][k])
 
 
+def test_vsource_extension_hb_diode(yb, golden):
+    """Netlist.vsource_extension: tests/HB_Diode.py written with add_vac instead of the hand-made current source + gyrator
+    pair gives the reference's golden result (same arrays, same solve)."""
+    g = golden('hb_diode')
+    y = yb.YalRF('Diode Testbench')
+    y.vsource_extension = True
+    y.add_vac('V1', 'n1', 'gnd', ac=5, freq=1e6)
+    y.add_resistor('R1', 'n1', 'n2', 100)
+    d1 = y.add_diode('D1', 'gnd', 'n2')
+    d1.options.update({'Is': 1e-15, 'N': 1, 'Area': 1})
+    hb = mthb('HB1', 1e6, 10)
+    conv, freqs, Vf, _, _ = hb.run(y)
+    assert conv
+    assert hb.last.levels() == g['iters'].tolist()
+    n2 = y.get_node_idx('n2') - 1
+    assert relmax(Vf[n2], g['Vf'][2]) < 1e-9        # the golden netlist's nodes: nx, n1, n2
+
+
 def test_linear_only_netlist_vs_oracle(yb):
     """Edge case: a netlist without any nonlinear device (R, C, L behind a gyrator source): hb_loop still runs its minimum
     of three iterations (:596) on a Jacobian that is the linear admittance alone; the DC analysis takes the linear branch

@@ -169,3 +169,37 @@ def test_linear_mthb_stamps_match_oracle():
                 for k in range(h['K'] + 1):
                     dev.add_mthb_stamps(Y, S, abs(o.freqs[k]), k)
         assert np.array_equal(Y, Yo)
+
+
+def test_vsource_extension_is_the_gyrator_idiom():
+    """Netlist.vsource_extension (off by default: add_vdc / add_vac raise like before): a voltage source is entered as the
+    current source + unit gyrator pair the reference's HB scripts write by hand, so the flattened arrays equal those of
+    the hand-written netlist; the returned handle forwards edits to the internal current source."""
+    import pytest
+    import yalrf_b200
+    from yalrf_b200._flatten import ParamBlock, Topology
+    y0 = yalrf_b200.Netlist('x')
+    with pytest.raises(NotImplementedError):
+        y0.add_vdc('V1', 'n1', 'gnd', 3.0)
+    ya = yalrf_b200.Netlist('a')                       # hand-written (tests/HB_Diode.py:12-15 + a floating DC source)
+    ya.add_iac('V1.I', 'V1.x', 'gnd', ac=5, freq=1e6)
+    ya.add_gyrator('V1.G', 'V1.x', 'n1', 'gnd', 'gnd', 1)
+    ya.add_resistor('R1', 'n1', 'n2', 100)
+    ya.add_idc('V2.I', 'V2.x', 'gnd', dc=0.3)
+    ya.add_gyrator('V2.G', 'V2.x', 'n2', 'n3', 'gnd', 1)
+    ya.add_diode('D1', 'gnd', 'n3')
+    yb = yalrf_b200.Netlist('b')
+    yb.vsource_extension = True
+    v1 = yb.add_vac('V1', 'n1', 'gnd', ac=5, freq=1e6)
+    yb.add_resistor('R1', 'n1', 'n2', 100)
+    v2 = yb.add_vdc('V2', 'n2', 'n3', 0.3)
+    yb.add_diode('D1', 'gnd', 'n3')
+    ta, tb = Topology(ya, 1, (10,)), Topology(yb, 1, (10,))
+    from yalrf_b200._flatten import source_kinds
+    assert ta.key(source_kinds(ta, 1e6, True), 0) == tb.key(source_kinds(tb, 1e6, True), 0)
+    pa, pb = ParamBlock(ta, 1e6, 1).finalize(), ParamBlock(tb, 1e6, 1).finalize()
+    for n in ('lin_val', 'src_val', 'diode_par'):
+        assert np.array_equal(getattr(pa, n), getattr(pb, n)), n
+    v2.dc = 0.5
+    v1.ac = 2.0
+    assert yb.get_device('V2.I').dc == 0.5 and yb.get_device('V1.I').ac == 2.0 and v2.dc == 0.5

@@ -310,3 +310,17 @@ class CubicNonLinearity(_Device):
 
     def __str__(self):
         return 'CubicNL: {}\nNodes = {} -> {}\n'.format(self.name, self.n1, self.n2)
+
+
+class VoltageSourceEquivalent:
+    """Handle of a voltage source entered as current source + unit gyrator (Netlist.vsource_extension): not a device of
+    its own -- the netlist holds the two internal devices -- but the object scripts edit between runs."""
+
+    def __init__(self, name, isrc, gyr):
+        self.name, self._i, self._g = name, isrc, gyr
+        self.n1, self.n2 = gyr.n2, gyr.n3
+
+    dc = property(lambda self: self._i.dc, lambda self, v: setattr(self._i, 'dc', v))
+    ac = property(lambda self: self._i.ac, lambda self, v: setattr(self._i, 'ac', v))
+    phase = property(lambda self: self._i.phase, lambda self, v: setattr(self._i, 'phase', v))
+    freq = property(lambda self: self._i.freq, lambda self, v: setattr(self._i, 'freq', v))

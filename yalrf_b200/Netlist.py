@@ -62,10 +62,33 @@ class Netlist():
             'MultiToneHarmonicBalance.py:692) and is outside this engine; model sources as current source + '
             'gyrator like the reference HB scripts do')
 
-    def add_vdc(self, *a, **k):
-        self._unsupported('VoltageSource')
+    # Extension (off by default = reference behaviour): with ``netlist.vsource_extension = True`` an ideal
+    # voltage source is entered the way the reference's HB scripts write it by hand (tests/HB_Diode.py:12-13) -- a current
+    # source of the same value into an internal node and a unit gyrator from that node to (n1, n2), which forces
+    # V(n1) - V(n2) = value -- instead of being refused.  The returned object forwards dc / ac / phase / freq to the
+    # internal current source, so scripts can keep editing the source between runs.
+    vsource_extension = False
 
-    add_vac = add_vsource = add_vpulse = add_vsine = add_vdc
+    def _vsource(self, name, n1, n2, itype, **kw):
+        if not self.vsource_extension:
+            self._unsupported('VoltageSource')
+        from .Devices import VoltageSourceEquivalent
+        x = name + '.x'
+        isrc = self._add(CurrentSource(name + '.I', self.add_node(x), 0, itype=itype, **kw))
+        gyr = self.add_gyrator(name + '.G', x, n1, n2, 'gnd', 1)
+        return VoltageSourceEquivalent(name, isrc, gyr)
+
+    def add_vdc(self, name, n1, n2, dc):
+        return self._vsource(name, n1, n2, 'dc', dc=dc)
+
+    def add_vac(self, name, n1, n2, ac, phase=0, freq=0):
+        """freq: the tone this source belongs to (the reference's VoltageSource has no frequency of its own)"""
+        return self._vsource(name, n1, n2, 'ac', ac=ac, phase=phase, freq=freq)
+
+    def add_vsource(self, *a, **k):
+        self._unsupported('VoltageSource with DC and AC values (the HB source vector ignores such sources, :652)')
+
+    add_vpulse = add_vsine = add_vsource
 
     def add_vcvs(self, *a, **k):
         self._unsupported('controlled source')
