@@ -66,13 +66,14 @@ def source_kinds(topo, freq, match_tones=True):
     return kinds
 
 
-def _zeros(shape, pinned):
-    """zeroed float64 host array; page-locked for large batches on a GPU box so that the H2D copies of
-    yhb_run_host are asynchronous DMA transfers instead of staged pageable copies"""
+def _zeros(shape, pinned, fill=True):
+    """float64 host array (zeroed unless the caller overwrites all of it); page-locked for large batches on a GPU box so
+    that the H2D copies of yhb_run_host are asynchronous DMA transfers instead of staged pageable copies"""
     if pinned:
         import torch
-        return torch.zeros(shape, dtype=torch.float64, pin_memory=True).numpy()
-    return np.zeros(shape)
+        make = torch.zeros if fill else torch.empty
+        return make(shape, dtype=torch.float64, pin_memory=True).numpy()
+    return np.zeros(shape) if fill else np.empty(shape)
 
 
 def _want_pinned(B):
@@ -123,7 +124,7 @@ class ParamBlock:
             cub[i] = dev.alpha
 
         def batch(row):
-            out = _zeros((B,) + row.shape, pinned)
+            out = _zeros((B,) + row.shape, pinned, fill=False)
             out[:] = row
             return out
 
