@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YHB_VERSION 200
+#define YHB_VERSION 210
 
 /* linear element kinds: the classes that implement add_mthb_stamps (MultiToneHarmonicBalance.py:686-695) */
 enum {
@@ -51,8 +51,11 @@ enum {
 /* raw diode model parameters, Diode.options (Diode.py:6-36); get_mthb_params uses the raw values */
 enum {
     YHB_DIODE_TEMP = 0, YHB_DIODE_IS, YHB_DIODE_N, YHB_DIODE_ISR, YHB_DIODE_NR, YHB_DIODE_IKF,
-    YHB_DIODE_BV, YHB_DIODE_IBV, YHB_DIODE_RS, YHB_DIODE_AREA, YHB_DIODE_NPAR
+    YHB_DIODE_BV, YHB_DIODE_IBV, YHB_DIODE_RS, YHB_DIODE_AREA,
+    YHB_DIODE_CJ0, YHB_DIODE_VJ, YHB_DIODE_M, YHB_DIODE_FC, YHB_DIODE_TT, YHB_DIODE_CP, YHB_DIODE_NPAR
 };
+/* CJ0 .. CP: junction / diffusion charge (Diode.py:207-235), used by the reference's AC and transient analyses only; in
+ * harmonic balance they count with YHB_FLAG_DIODE_CHARGE */
 
 /* raw BJT model parameters, BJT.options (BJT.py:5-52) + polarity (BJT.py:71) */
 enum {
@@ -65,6 +68,8 @@ enum {
 
 #define YHB_FLAG_PNP_EXTENSION 1  /* honour BJT polarity in HB (the reference ignores it, BJT.py:495-503) */
 #define YHB_FLAG_EXACT_JACOBIAN 2 /* re-zero dQdV every iteration (the reference accumulates it, :413/:438) */
+#define YHB_FLAG_DIODE_CHARGE 512 /* extension: diodes carry charge in HB, Qd = Cp Vd + Tt Id + Qj(Vd), Cd = Cp + Tt gd + Cj(Vd)
+                                     (the reference's MTHB stamps diode conductance and current only, :441-475) */
 
 #define YHB_FLAG_NO_PEEL 4        /* factor the full W x W system (no structural peeling of ideal-source rows) */
 #define YHB_FLAG_NO_BAND 16       /* staged engine: dense core storage even when the core is block banded over nodes */

@@ -179,7 +179,7 @@ def exp_lim(x):
         return np.where(x < 200., np.exp(np.minimum(x, 200.)), np.exp(200.) + np.exp(200.) * (x - 200.))
 
 
-def diode_mthb_params(opt, Vd, Vdold):
+def diode_mthb_params(opt, Vd, Vdold, with_vlim=False):
     """Diode.get_mthb_params, Diode.py:395-427 (raw options: no Area scaling, no Rs, no charge)."""
     Is, N, Isr, Nr = opt['Is'], opt['N'], opt['Isr'], opt['Nr']
     Ikf, Bv, Ibv, T = opt['Ikf'], opt['Bv'], opt['Ibv'], opt['Temp']
@@ -205,7 +205,23 @@ def diode_mthb_params(opt, Vd, Vdold):
 
     Id = Idf + Idr + Ibr
     gd = gdf + gdr + gbr
+    if with_vlim:
+        return gd, Id, Vd
     return gd, Id
+
+
+def diode_charge_params(opt, Vd, gd, Id):
+    """Extension (diode_charge=True; the reference's MTHB has no diode charge): Diode.calc_oppoint's charge model,
+    Diode.py:207-235 -- Cd = Cp + Tt gd + Cj, Qd = Cp Vd + Tt Id + Qj, Cj0 scaled by Area (Diode.py:95); Vd is the
+    LIMITED junction voltage get_mthb_params worked with."""
+    Cj0 = opt['Cj0'] * opt['Area']
+    Cj = pn_capacitance(Vd, Cj0, opt['Vj'], opt['M'], opt['Fc'])
+    Qj = pn_charge(Vd, Cj0, opt['Vj'], opt['M'], opt['Fc'])
+    if Cj0 == 0.:
+        Cj, Qj = np.zeros_like(np.asarray(Vd, dtype=float)), np.zeros_like(np.asarray(Vd, dtype=float))
+    Cd = opt['Cp'] + opt['Tt'] * gd + Cj
+    Qd = opt['Cp'] * Vd + opt['Tt'] * Id + Qj
+    return Cd, Qd
 
 
 def cubic_mthb_params(alpha, V):
@@ -732,13 +748,14 @@ class HBOracle:
     behaviour.
     """
 
-    def __init__(self, name, freq=1e9, numharmonics=10, pnp_extension=False, exact_jacobian=False):
+    def __init__(self, name, freq=1e9, numharmonics=10, pnp_extension=False, exact_jacobian=False, diode_charge=False):
         self.name = name
         self.freq = freq
         self.numharmonics = numharmonics
         self.options = HB_OPTIONS.copy()
         self.pnp_extension = pnp_extension
         self.exact_jacobian = exact_jacobian
+        self.diode_charge = diode_charge     # extension: diodes carry charge in HB (see diode_charge_params)
         self.trace = None        # set to a list to record (J, F, dV, V) per Newton iteration
         self.level_log = []      # [(alpha, iterations, converged, total_error)] of the last run
         self.total_newton = 0
@@ -948,7 +965,18 @@ class HBOracle:
                 vd = node_wave(vt, n1) - node_wave(vt, n2)
                 vdold = node_wave(vtprev, n1) - node_wave(vtprev, n2)
                 if dev.kind == 'diode':
-                    gd, Id = diode_mthb_params(dev.options, vd, vdold)
+                    gd, Id, vlim = diode_mthb_params(dev.options, vd, vdold, with_vlim=True)
+                    if self.diode_charge:  # extension: fresh every iteration (dQd is zeroed by hb_loop), never accumulated
+                        Cd, Qd = diode_charge_params(dev.options, vlim, gd, Id)
+                        cf = self._block(np.asarray(Cd, dtype=float))
+                        Qd = np.asarray(Qd, dtype=float).reshape(S, 1)
+                        for na, sg in ((n1, +1.), (n2, -1.)):
+                            if na >= 0:
+                                qt[na * S:(na + 1) * S] += sg * Qd
+                                self.dQd[na * S:(na + 1) * S, na * S:(na + 1) * S] += cf
+                        if n1 >= 0 and n2 >= 0:
+                            self.dQd[n1 * S:(n1 + 1) * S, n2 * S:(n2 + 1) * S] -= cf
+                            self.dQd[n2 * S:(n2 + 1) * S, n1 * S:(n1 + 1) * S] -= cf
                 else:
                     gd, Id = cubic_mthb_params(dev.alpha, vd)
                 Id = np.asarray(Id, dtype=float).reshape(S, 1)
@@ -1025,8 +1053,10 @@ class HBOracle:
             qt[:] = 0
             if self.exact_jacobian:
                 dQdV[:, :] = 0
+            if self.diode_charge:
+                self.dQd = np.zeros((W, W))
             self.eval_devices(vt, vtprev, dIdV, dQdV, it, qt)
-            J = Y + dIdV + self.apply_omega(dQdV)
+            J = Y + dIdV + self.apply_omega(dQdV + self.dQd if self.diode_charge else dQdV)
             Il = Y @ V - Is
             Inl = self.fft(it) + self.apply_omega(self.fft(qt))
             F = Il + Inl

@@ -1052,3 +1052,31 @@ def test_linear_only_netlist_vs_oracle(yb):
     assert res.converged.tolist() == [1, 1, 1]
     assert relmax(res.V[2], o.V[:, 0]) < 1e-9
     assert relmax(res.V[0] * 4.0, res.V[2]) < 1e-12          # linear circuit: the response scales with the drive
+
+
+def test_diode_charge_extension_vs_oracle(yb):
+    """hb.diode_charge = True -- diodes carry the charge of Diode.calc_oppoint (Diode.py:207-235: Cp, Tt,
+    Cj0 / Vj / M / Fc) in harmonic balance, which the reference's MTHB leaves out (:441-475).  Opt-in extension, parity
+    unpinned by the reference: checked against the oracle with the same extension (single tone and two tones), identical
+    iteration counts, phasors within 1e-9; off by default (the golden HB_Diode result is untouched)."""
+    from oracle import hb_oracle as ho
+    strong = {'Cj0': 2e-9, 'Vj': 0.8, 'M': 0.4, 'Fc': 0.5, 'Tt': 1e-7, 'Cp': 1e-10, 'Area': 2.0}
+    mild = {'Cj0': 2e-10, 'Vj': 0.8, 'M': 0.4, 'Fc': 0.5, 'Tt': 1e-8, 'Cp': 1e-11, 'Area': 2.0}   # the two-tone ladder backs off twice
+    for build, nh, charge in ((circuits.hb_diode, None, strong), (circuits.hb_diode_two_tones, [3, 3], mild)):
+        y = yb.YalRF('Diode Testbench')
+        h = build(y)
+        h['d1'].options.update(charge)
+        hb = mthb('HB1', h['freq'], nh if nh is not None else h['K'])
+        hb.diode_charge = True
+        conv, freqs, Vf, _, _ = hb.run(y)
+        yo = ho.FlatNetlist()
+        ho_h = build(yo)
+        ho_h['d1'].options.update(charge)
+        o = ho.HBOracle('HB1', h['freq'], nh if nh is not None else h['K'], diode_charge=True)
+        conv_o = o.run(yo)[0]
+        assert conv and conv_o
+        assert hb.last.levels() == [l[1] for l in o.level_log]
+        assert relmax(hb.V, o.V) < 1e-9
+        hb0 = mthb('HB1', h['freq'], nh if nh is not None else h['K'])       # extension off: the charge parameters are ignored
+        assert hb0.run(y)[0]
+        assert relmax(hb0.V, hb.V) > 1e-4

@@ -20,8 +20,8 @@ def test_library_exports_header_symbols():
     assert names >= set(_lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.yhb_version() == 200
-    assert _lib.DIODE_NPAR == 10 and _lib.BJT_NPAR == 32
+    assert lib.yhb_version() == 210
+    assert _lib.DIODE_NPAR == 16 and _lib.BJT_NPAR == 32
 
 
 def test_header_enums_match_binding():
@@ -31,7 +31,7 @@ def test_header_enums_match_binding():
     names = ['Temp'] + [x.strip().split('_')[-1].capitalize() for x in re.findall(r'YHB_BJT_[A-Z]+', body)]
     assert [n.lower() for n in names] == [n.lower() for n in _lib.BJT_PARAMS]
     body = re.search(r'YHB_DIODE_TEMP = 0,(.*?)YHB_DIODE_NPAR', hdr, re.S).group(1)
-    names = ['Temp'] + [x.strip().split('_')[-1].capitalize() for x in re.findall(r'YHB_DIODE_[A-Z]+', body)]
+    names = ['Temp'] + [x.strip().split('_')[-1].capitalize() for x in re.findall(r'YHB_DIODE_[A-Z0-9]+', body)]
     assert [n.lower() for n in names] == [n.lower() for n in _lib.DIODE_PARAMS]
 
 

@@ -28,6 +28,7 @@ class MultiToneHarmonicBalance:
         # extensions, off by default = reference behaviour
         self.pnp_extension = False    # honour BJT polarity in HB (reference: every BJT is NPN, BJT.py:495-503)
         self.exact_jacobian = False   # re-zero dQdV each iteration (reference accumulates it, :413)
+        self.diode_charge = False     # diodes carry their junction / diffusion charge in HB (reference: g and I only, :441-475)
         self.verbose = False          # print the reference's per-level log lines (:354, :358, :383-384, :597-598)
         self.engine = 'auto'          # 'auto': fused on-chip engine when the circuit fits one SM; 'staged': HBM Jacobian
         self.peel = True              # eliminate ideal-source rows symbolically before the dense factorisation
@@ -44,7 +45,7 @@ class MultiToneHarmonicBalance:
 
     # ------------------------------------------------------------------ helpers
     def _flags(self):
-        return ((L.FLAG_PNP_EXTENSION if self.pnp_extension else 0) | (L.FLAG_EXACT_JACOBIAN if self.exact_jacobian else 0) |
+        return ((L.FLAG_PNP_EXTENSION if self.pnp_extension else 0) | (L.FLAG_EXACT_JACOBIAN if self.exact_jacobian else 0) | (L.FLAG_DIODE_CHARGE if self.diode_charge else 0) |
                 (0 if self.peel else L.FLAG_NO_PEEL) | (L.FLAG_STAGED if self.engine == 'staged' else 0) |
                 (0 if self.band else L.FLAG_NO_BAND) |
                 (L.FLAG_BLOCK_THOMAS if self.block_thomas else 0) |

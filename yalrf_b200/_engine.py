@@ -297,7 +297,7 @@ def to_time(Vf, freqs, t):
         raise RuntimeError('yalrf_b200 needs a CUDA device: there is no CPU fallback')
     Vf = np.ascontiguousarray(Vf, dtype=np.complex128)
     B, N, K1 = Vf.shape
-    f = np.ascontiguousarray(np.broadcast_to(np.asarray(freqs, dtype=np.float64), (B, K1)))
+    f = np.array(np.broadcast_to(np.asarray(freqs, dtype=np.float64), (B, K1)))   # a writable, contiguous copy
     t = np.ascontiguousarray(t, dtype=np.float64)
     dev = torch.device('cuda', torch.cuda.current_device())
     L.check(L.lib().yhb_set_device(dev.index))

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get('YHB_LIB', os.path.join(_HERE, 'libyhb.so'))  # YHB_LI
 # enums of include/yhb.h
 LIN_RESISTOR, LIN_CAPACITOR, LIN_INDUCTOR, LIN_GYRATOR, LIN_IHF = range(5)
 SRC_DC, SRC_AC1, SRC_AC2, SRC_DC_ONLY = range(4)
-DIODE_PARAMS = ['Temp', 'Is', 'N', 'Isr', 'Nr', 'Ikf', 'Bv', 'Ibv', 'Rs', 'Area']
+DIODE_PARAMS = ['Temp', 'Is', 'N', 'Isr', 'Nr', 'Ikf', 'Bv', 'Ibv', 'Rs', 'Area', 'Cj0', 'Vj', 'M', 'Fc', 'Tt', 'Cp']
 BJT_PARAMS = ['Temp', 'Is', 'Nf', 'Nr', 'Ikf', 'Ikr', 'Vaf', 'Var', 'Ise', 'Ne', 'Isc', 'Nc', 'Bf', 'Br',
               'Cje', 'Vje', 'Mje', 'Cjc', 'Vjc', 'Mjc', 'Xcjc', 'Cjs', 'Vjs', 'Mjs', 'Fc', 'Tf', 'Xtf', 'Vtf',
               'Itf', 'Tr', 'Area', 'type']
@@ -25,6 +25,7 @@ FLAG_BLOCK_THOMAS = 32
 FLAG_NO_BLOCK_THOMAS = 64
 FLAG_NO_BLOCK_SPARSE = 128
 FLAG_BLOCK_SPARSE = 256
+FLAG_DIODE_CHARGE = 512
 ENGINES = ['fused', 'staged-dense', 'staged-banded', 'staged-block-thomas']
 MAX_LEVELS = 64
 

@@ -413,7 +413,8 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
     // waveform slots: device order inside the evaluation kernel is diodes, cubics, bjts
     std::vector<int> wave_base;
     int nw = 0;
-    for (int i = 0; i < d.nd; ++i) { wave_base.push_back(nw); nw += 2; }
+    const bool dq = (desc->flags & YHB_FLAG_DIODE_CHARGE) != 0;  // diodes: g, I and, with the charge extension, c, q
+    for (int i = 0; i < d.nd; ++i) { wave_base.push_back(nw); nw += dq ? 4 : 2; }
     for (int i = 0; i < d.nc; ++i) { wave_base.push_back(nw); nw += 2; }
     for (int i = 0; i < d.nb; ++i) { wave_base.push_back(nw); nw += kBjtWaves; }
     d.nwave = nw;
@@ -445,6 +446,15 @@ extern "C" int yhb_plan_create(const yhb_plan_desc *desc, yhb_plan **out) {
             if (n2 > 0) ni.add(n2 - 1, wb + 1, -1);
             g_stamp(n1, n2, wb, -1);
             g_stamp(n2, n1, wb, -1);
+            if (kind == 0 && dq) {  // charge extension: capacitance slot 4 nb + i (the BJT slots are 4 q + j), charge wave wb + 3
+                const int slot = 4 * d.nb + i;
+                c_stamp(n1, n1, slot, +1);
+                c_stamp(n2, n2, slot, +1);
+                c_stamp(n1, n2, slot, -1);
+                c_stamp(n2, n1, slot, -1);
+                if (n1 > 0) nq.add(n1 - 1, wb + 3, +1);
+                if (n2 > 0) nq.add(n2 - 1, wb + 3, -1);
+            }
         } else {
             const int *nd = &pl->bjt_nodes[3 * i];
             int wb = wave_base[d.nd + d.nc + i];

@@ -24,64 +24,6 @@ __device__ __forceinline__ double exp_lim(double x) {
     return (x < 200.) ? exp(x) : e200 + e200 * (x - 200.);
 }
 
-struct DiodeDerived {
-    double lim;         // 10 N Vt
-    double nvt, nrvt;   // N Vt, Nr Vt
-    double Is, Isr;     // raw (Diode.py:396-398)
-    double gdf0, gdr0;  // Is/(N Vt), Isr/(Nr Vt)
-    double Ikf, Bv, Ibv, vt;
-    double ibr0, gbr0;  // Ibv*exp_lim(-Bv/Vt), Ibv/Vt
-    int has_ikf, has_bv;
-};
-
-__device__ inline void diode_derive(const double *p, DiodeDerived &d) {
-    double Vt = YHB_K_BOLTZ * p[YHB_DIODE_TEMP] / YHB_Q_ELEM;
-    double N = p[YHB_DIODE_N], Nr = p[YHB_DIODE_NR];
-    d.vt = Vt;
-    d.lim = 10. * N * Vt;
-    d.nvt = N * Vt;
-    d.nrvt = Nr * Vt;
-    d.Is = p[YHB_DIODE_IS];
-    d.Isr = p[YHB_DIODE_ISR];
-    d.gdf0 = d.Is / (N * Vt);
-    d.gdr0 = d.Isr / (Nr * Vt);
-    d.Ikf = p[YHB_DIODE_IKF];
-    d.Bv = p[YHB_DIODE_BV];
-    d.Ibv = p[YHB_DIODE_IBV];
-    d.has_ikf = isfinite(d.Ikf);
-    d.has_bv = isfinite(d.Bv);
-    d.ibr0 = d.has_bv ? d.Ibv * exp_lim(-d.Bv / Vt) : 0.;
-    d.gbr0 = d.Ibv / Vt;
-}
-
-// returns (gd, Id); Vd / Vdold are the unlimited junction voltages of this and the previous iterate
-__device__ inline void diode_eval(const DiodeDerived &d, double Vd, double Vdold, double &gd, double &Id) {
-    Vd = Vdold + d.lim * tanh((Vd - Vdold) / d.lim);  // Diode.py:407
-    double ef = exp_lim(Vd / d.nvt);
-    double er = exp_lim(Vd / d.nrvt);
-    double Idf = d.Is * (ef - 1.);
-    double Idr = d.Isr * (er - 1.);
-    double gdf = d.gdf0 * ef;
-    double gdr = d.gdr0 * er;
-    if (d.has_ikf) {  // Diode.py:414-416 (gdf uses the already-scaled Idf, as written)
-        Idf = Idf * sqrt(d.Ikf / (d.Ikf + Idf));
-        gdf = gdf * (1. - 0.5 * Idf / (d.Ikf + Idf)) * sqrt(d.Ikf / (d.Ikf + Idf));
-    }
-    double Ibr = 0., gbr = 0.;
-    if (d.has_bv) {  // Diode.py:420-422
-        Ibr = d.ibr0 * (1. - exp_lim(-Vd / d.vt));
-        gbr = d.gbr0 * exp_lim(-(d.Bv + Vd) / d.vt);
-    }
-    Id = Idf + Idr + Ibr;
-    gd = gdf + gdr + gbr;
-}
-
-// CubicNonLinearity.py:36-41 (g = 2 alpha V^2 as written in the reference)
-__device__ __forceinline__ void cubic_eval(double alpha, double V, double &g, double &I) {
-    g = 2 * alpha * V * V;
-    I = alpha * V * V * V;
-}
-
 struct PnJunction {  // BJT.py:591-608 with sample-invariant factors hoisted
     double Cj, Vj, Mj, fcvj;
     double c2, den;         // Cj / (1-Fc)^Mj ; Vj (1-Fc)
@@ -125,6 +67,81 @@ __device__ inline void pn_eval(const PnJunction &j, double V, double &C, double 
         double X = j.X0 + j.X1 * (r - j.fc) + j.X2 * (r * r - j.fc2);
         Q = j.cjvj * X;
     }
+}
+
+struct DiodeDerived {
+    double lim;         // 10 N Vt
+    double nvt, nrvt;   // N Vt, Nr Vt
+    double Is, Isr;     // raw (Diode.py:396-398)
+    double gdf0, gdr0;  // Is/(N Vt), Isr/(Nr Vt)
+    double Ikf, Bv, Ibv, vt;
+    double ibr0, gbr0;  // Ibv*exp_lim(-Bv/Vt), Ibv/Vt
+    int has_ikf, has_bv;
+    PnJunction j;       // depletion charge (YHB_FLAG_DIODE_CHARGE; Cj0 scaled by Area like Diode.init does, Diode.py:95)
+    double Tt, Cp;
+};
+
+__device__ inline void diode_derive(const double *p, DiodeDerived &d) {
+    double Vt = YHB_K_BOLTZ * p[YHB_DIODE_TEMP] / YHB_Q_ELEM;
+    double N = p[YHB_DIODE_N], Nr = p[YHB_DIODE_NR];
+    d.vt = Vt;
+    d.lim = 10. * N * Vt;
+    d.nvt = N * Vt;
+    d.nrvt = Nr * Vt;
+    d.Is = p[YHB_DIODE_IS];
+    d.Isr = p[YHB_DIODE_ISR];
+    d.gdf0 = d.Is / (N * Vt);
+    d.gdr0 = d.Isr / (Nr * Vt);
+    d.Ikf = p[YHB_DIODE_IKF];
+    d.Bv = p[YHB_DIODE_BV];
+    d.Ibv = p[YHB_DIODE_IBV];
+    d.has_ikf = isfinite(d.Ikf);
+    d.has_bv = isfinite(d.Bv);
+    d.ibr0 = d.has_bv ? d.Ibv * exp_lim(-d.Bv / Vt) : 0.;
+    d.gbr0 = d.Ibv / Vt;
+    pn_derive(p[YHB_DIODE_CJ0] * p[YHB_DIODE_AREA], p[YHB_DIODE_VJ], p[YHB_DIODE_M], p[YHB_DIODE_FC], d.j);
+    d.Tt = p[YHB_DIODE_TT];
+    d.Cp = p[YHB_DIODE_CP];
+}
+
+// returns (gd, Id); Vd / Vdold are the unlimited junction voltages of this and the previous iterate
+__device__ inline void diode_eval(const DiodeDerived &d, double Vd, double Vdold, double &gd, double &Id, double *Vlim = nullptr) {
+    Vd = Vdold + d.lim * tanh((Vd - Vdold) / d.lim);  // Diode.py:407
+    if (Vlim) *Vlim = Vd;
+    double ef = exp_lim(Vd / d.nvt);
+    double er = exp_lim(Vd / d.nrvt);
+    double Idf = d.Is * (ef - 1.);
+    double Idr = d.Isr * (er - 1.);
+    double gdf = d.gdf0 * ef;
+    double gdr = d.gdr0 * er;
+    if (d.has_ikf) {  // Diode.py:414-416 (gdf uses the already-scaled Idf, as written)
+        Idf = Idf * sqrt(d.Ikf / (d.Ikf + Idf));
+        gdf = gdf * (1. - 0.5 * Idf / (d.Ikf + Idf)) * sqrt(d.Ikf / (d.Ikf + Idf));
+    }
+    double Ibr = 0., gbr = 0.;
+    if (d.has_bv) {  // Diode.py:420-422
+        Ibr = d.ibr0 * (1. - exp_lim(-Vd / d.vt));
+        gbr = d.gbr0 * exp_lim(-(d.Bv + Vd) / d.vt);
+    }
+    Id = Idf + Idr + Ibr;
+    gd = gdf + gdr + gbr;
+}
+
+// CubicNonLinearity.py:36-41 (g = 2 alpha V^2 as written in the reference)
+__device__ __forceinline__ void cubic_eval(double alpha, double V, double &g, double &I) {
+    g = 2 * alpha * V * V;
+    I = alpha * V * V * V;
+}
+
+// Extension (YHB_FLAG_DIODE_CHARGE): the diode's charge and capacitance as the reference's own operating-point code
+// writes them (Diode.calc_oppoint, Diode.py:207-235): Cd = Cp + Tt gd + Cj, Qd = Cp Vd + Tt Id + Qj, with the depletion
+// pair (Cj, Qj) of Diode.py:219-228 (the shape of BJT.py:591-608).
+// Vd: the LIMITED junction voltage diode_eval worked with (Vd = Vdold + lim tanh(...)), gd / Id its results
+__device__ inline void diode_charge_eval(const DiodeDerived &d, double Vd, double gd, double Id, double &Cd, double &Qd) {
+    double Cj, Qj;
+    pn_eval(d.j, Vd, Cj, Qj);
+    Cd = d.Cp + d.Tt * gd + Cj;
+    Qd = d.Cp * Vd + d.Tt * Id + Qj;
 }
 
 struct BjtDerived {
