@@ -1080,3 +1080,34 @@ def test_diode_charge_extension_vs_oracle(yb):
         hb0 = mthb('HB1', h['freq'], nh if nh is not None else h['K'])       # extension off: the charge parameters are ignored
         assert hb0.run(y)[0]
         assert relmax(hb0.V, hb.V) > 1e-4
+
+
+def test_diode_rs_extension_vs_oracle(yb):
+    """hb.diode_rs = True -- a diode's series resistance counts (internal node + resistor Rs / Area; the
+    reference's get_mthb_params ignores Rs).  Against the oracle on the netlist written out by hand; the netlist's own
+    node indices do not move; off by default."""
+    from oracle import hb_oracle as ho
+    y = yb.YalRF('Diode Testbench')
+    h = circuits.hb_diode(y)
+    h['d1'].options.update({'Rs': 5.0, 'Area': 2.0})
+    hb = mthb('HB1', h['freq'], h['K'])
+    hb.diode_rs = True
+    conv, freqs, Vf, _, _ = hb.run(y)
+    yo = ho.FlatNetlist()
+    yo.add_iac('I1', 'nx', 'gnd', ac=5.0, freq=1e6)
+    yo.add_gyrator('G1', 'nx', 'n1', 'gnd', 'gnd', 1)
+    yo.add_resistor('R1', 'n1', 'n2', 100)
+    yo.add_resistor('D1.Rs', 'gnd', 'D1.rs', 2.5)
+    d = yo.add_diode('D1', 'D1.rs', 'n2')
+    d.options.update({'Is': 1e-15, 'N': 1, 'Area': 2.0, 'Rs': 0.0})
+    o = ho.HBOracle('HB1', h['freq'], h['K'])
+    assert conv and o.run(yo)[0]
+    assert hb.N == 4 and hb.get_node_idx('n2') == 2 and hb.get_node_idx('D1.rs') == 3
+    assert hb.last.levels() == [l[1] for l in o.level_log]
+    assert relmax(hb.V, o.V) < 1e-9
+    hb0 = mthb('HB1', h['freq'], h['K'])
+    assert hb0.run(y)[0] and hb0.N == 3
+    assert relmax(hb0.Vf[2], Vf[2]) > 1e-3               # Rs = 2.5 ohm in series with the diode changes n2 visibly
+    # an Is sweep of the original diode reaches its twin
+    res = hb.run_sweep(y, [(h['d1'], 'Is', np.array([1e-15, 2e-15]))])
+    assert res.converged.tolist() == [1, 1] and relmax(res.V[0], o.V[:, 0]) < 1e-9 and relmax(res.V[1], res.V[0]) > 1e-6

@@ -18,6 +18,40 @@ options['abstol'] = 1e-6
 options['maxiter'] = 100
 
 
+class _RsZeroOptions:
+    """read-through view of a diode's options with Rs = 0 (the series resistance is a device of its own then)"""
+
+    def __init__(self, base):
+        self.base = base
+
+    def __getitem__(self, k):
+        return 0.0 if k == 'Rs' else self.base[k]
+
+    def keys(self):
+        return self.base.keys()
+
+
+def _expand_diode_rs(netlist):
+    """Extension (hb.diode_rs): a copy of the netlist in which every diode with Rs > 0 is a resistor Rs / Area (Diode.init,
+    Diode.py:96) from its anode to an internal node -- appended behind the netlist's own nodes, so their indices stay --
+    in series with a twin of the diode that reads the same options with Rs = 0."""
+    from ..Devices import Diode, Resistor
+    out = netlist.copy()
+    devs = []
+    for dev in out.devices:
+        if dev.kind == 'diode' and float(dev.options['Rs']) > 0.:
+            ni = out.add_node(dev.name + '.rs')
+            devs.append(Resistor(dev.name + '.Rs', dev.n1, ni, float(dev.options['Rs']) / float(dev.options['Area'])))
+            twin = Diode(dev.name, ni, dev.n2)
+            twin.options = _RsZeroOptions(dev.options)
+            twin._options_of = dev.options      # sweeps of the original diode's options reach the twin (ParamBlock.set)
+            devs.append(twin)
+        else:
+            devs.append(dev)
+    out.devices = devs
+    return out
+
+
 class MultiToneHarmonicBalance:
 
     def __init__(self, name, freq=1e9, numharmonics=10):
@@ -29,6 +63,8 @@ class MultiToneHarmonicBalance:
         self.pnp_extension = False    # honour BJT polarity in HB (reference: every BJT is NPN, BJT.py:495-503)
         self.exact_jacobian = False   # re-zero dQdV each iteration (reference accumulates it, :413)
         self.diode_charge = False     # diodes carry their junction / diffusion charge in HB (reference: g and I only, :441-475)
+        self.diode_rs = False         # a diode's series resistance Rs counts in DC and HB: an internal node + a resistor Rs / Area
+                                      # (the reference's get_mthb_params ignores Rs, Diode.py:395-427); run / run_batch / run_sweep
         self.verbose = False          # print the reference's per-level log lines (:354, :358, :383-384, :597-598)
         self.engine = 'auto'          # 'auto': fused on-chip engine when the circuit fits one SM; 'staged': HBM Jacobian
         self.peel = True              # eliminate ideal-source rows symbolically before the dense factorisation
@@ -54,7 +90,7 @@ class MultiToneHarmonicBalance:
                 (L.FLAG_NO_BLOCK_SPARSE if self.block_sparse is False else 0))
 
     def _setup(self, netlist):
-        self.netlist = netlist.copy()
+        self.netlist = _expand_diode_rs(netlist) if self.diode_rs else netlist.copy()
         self.lin_devs = self.netlist.get_linear_devices()
         self.nonlin_devs = self.netlist.get_nonlinear_devices()
         plan, topo = E.get_plan(self.netlist, self.freq, self.numharmonics, self._flags())

@@ -160,7 +160,9 @@ class ParamBlock:
         if hasattr(dev, 'options'):
             # users share one options dict between devices (q2.options = q1.options, tests/HB_DiffAmp.py:67-69)
             for i, (_, d) in enumerate(t.diodes):
-                if d.options is dev.options and field in L.DIODE_PARAMS:
+                if (d.options is dev.options or getattr(d, '_options_of', None) is dev.options) and field in L.DIODE_PARAMS:
+                    if field == 'Rs' and getattr(d, '_options_of', None) is not None:
+                        raise KeyError('Rs of a diode expanded by hb.diode_rs is a resistor of its own: sweep that instead')
                     self.diode_par[:, i, L.DIODE_PARAMS.index(field)] = values
                     hit = True
             for i, (_, d) in enumerate(t.bjts):
