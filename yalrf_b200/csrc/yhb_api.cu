@@ -78,6 +78,13 @@ static FusedChoice fused_choice(const PlanDev &d) {
             const size_t c = (fused_lin_cache_doubles(d) + 2) * sizeof(double);
             return b + c <= lim3 ? FusedChoice{true, kFusedBsNT, b + c, 3} : FusedChoice{true, kFusedBsNT, b, 1};
         }
+        // too large for three CTAs per SM: the compact variant with TWO CTAs per SM (192 threads each) instead of the
+        // dense-core variant's 32 NT threads, most of which wait at barriers while the block-sparse solve runs
+        // (ActiveLoad DiffAmp, 27 nonlinear pairs, 99 KB: 178 k -> 188 k solves/s against k_fused<11> on 352 threads)
+        if (b <= lim2 && !getenv("YHB_NO_BS_COMPACT2")) {
+            const size_t c = (fused_lin_cache_doubles(d) + 2) * sizeof(double);
+            return b + c <= lim2 ? FusedChoice{true, kFusedBsNT, b + c, 3} : FusedChoice{true, kFusedBsNT, b, 1};
+        }
     }
     for (int hot = 1; hot >= 0; --hot) {
 #define YHB_CASE(t)                                                                 \
