@@ -182,10 +182,31 @@ def colpitts_nvec_fixture(Netlist, MTHB, save):
     save('colpitts_nvec', nvec=nvec, fosc=np.array(fosc), Vosc=np.array(vosc), vtank=np.array(vtank), Vf=np.array(Vfs))
 
 
+def diode_charge_fixture(Netlist, MTHB, save):
+    """The reference's own diode charge model (Diode.calc_oppoint, Diode.py:207-235: what its AC / transient analyses use)
+    at 96 junction voltages on both sides of Fc Vj: pins the model the hb.diode_charge extension evaluates in HB.
+        python tests/golden/make_golden.py --diode-charge"""
+    y = Netlist('d')
+    d = y.add_diode('D1', 'n1', 'gnd')
+    opt = {'Is': 2e-14, 'N': 1.1, 'Cj0': 2e-9, 'Vj': 0.8, 'M': 0.4, 'Fc': 0.5, 'Tt': 1e-7, 'Cp': 1e-10, 'Area': 2.0}
+    d.options.update(opt)
+    d.init()
+    vd = np.linspace(-3.0, 0.75, 96)
+    out = np.zeros((96, 5))
+    for i, v in enumerate(vd):
+        d.It, d.gt = 0., 0.          # Rs = 0: the junction voltage is the terminal voltage (calc_dc, Diode.py:251-255)
+        d.calc_oppoint(np.array([v]), usevlimit=False)
+        out[i] = [d.oppoint['Vd'], d.oppoint['gd'], d.oppoint['Id'], d.oppoint['Cd'], d.oppoint['Qd']]
+    names = sorted(d.options.keys())
+    save('diode_charge_model', vd=vd, out=out, opt_names=np.array(names), opt_vals=np.array([float(d.options[k]) for k in names]))
+
+
 def main():
     import circuits
     Netlist, MTHB = import_reference()
     out = {}
+    if '--diode-charge' in sys.argv:
+        return diode_charge_fixture(Netlist, MTHB, save_npz)
     if '--osc-root' in sys.argv:
         return osc_root_fixture(Netlist, MTHB, save_npz)
     if '--colpitts-nvec' in sys.argv:

@@ -203,3 +203,33 @@ def test_vsource_extension_is_the_gyrator_idiom():
     v2.dc = 0.5
     v1.ac = 2.0
     assert yb.get_device('V2.I').dc == 0.5 and yb.get_device('V1.I').ac == 2.0 and v2.dc == 0.5
+
+
+def test_diode_rs_expansion_is_the_hand_written_netlist():
+    """hb.diode_rs: the expanded netlist flattens to the arrays of the netlist written out by hand (resistor Rs / Area to an
+    internal node behind the netlist's own nodes + a diode with Rs = 0); option sweeps of the original diode reach the twin."""
+    import pytest
+    import yalrf_b200
+    from yalrf_b200.Analyses.MultiToneHarmonicBalance import _expand_diode_rs
+    from yalrf_b200._flatten import ParamBlock, Topology, source_kinds
+    ya = yalrf_b200.Netlist('a')
+    h = circuits.hb_diode(ya)
+    h['d1'].options.update({'Rs': 5.0, 'Area': 2.0})
+    ye = _expand_diode_rs(ya)
+    assert ya.get_num_nodes() == 4 and ye.get_num_nodes() == 5 and ye.get_node_idx('n2') == ya.get_node_idx('n2')
+    yb = yalrf_b200.Netlist('b')
+    yb.add_iac('I1', 'nx', 'gnd', ac=5.0, freq=1e6)
+    yb.add_gyrator('G1', 'nx', 'n1', 'gnd', 'gnd', 1)
+    yb.add_resistor('R1', 'n1', 'n2', 100)
+    yb.add_resistor('D1.Rs', 'gnd', 'D1.rs', 2.5)
+    d = yb.add_diode('D1', 'D1.rs', 'n2')
+    d.options.update({'Is': 1e-15, 'N': 1, 'Area': 2.0, 'Rs': 0.0})
+    te, tb = Topology(ye, 1, (10,)), Topology(yb, 1, (10,))
+    assert te.key(source_kinds(te, 1e6, True), 0) == tb.key(source_kinds(tb, 1e6, True), 0)
+    pe, pb = ParamBlock(te, 1e6, 2), ParamBlock(tb, 1e6, 2)
+    pe.set(h['d1'], 'Is', [1e-15, 3e-15])
+    pb.set(d, 'Is', [1e-15, 3e-15])
+    for n in ('lin_val', 'src_val', 'diode_par'):
+        assert np.array_equal(getattr(pe.finalize(), n), getattr(pb.finalize(), n)), n
+    with pytest.raises(KeyError):
+        pe.set(h['d1'], 'Rs', [1.0, 2.0])

@@ -278,3 +278,14 @@ def colpitts_tolerance():
     sens = max(relmax(run(e), a) for e in (2.3e-16, -2.3e-16))
     assert 1e-10 < sens < 1e-6, sens          # it IS a sensitive case, and not a broken one
     return max(1e-9, 20 * sens)
+
+
+def test_diode_charge_model(golden):
+    """hb.diode_charge extension: the charge model it evaluates is the reference's own Diode.calc_oppoint (Diode.py:207-235),
+    96 junction voltages on both sides of Fc Vj, given the reference's (Vd, gd, Id)."""
+    g = golden('diode_charge_model')
+    opt = dict(zip(g['opt_names'].tolist(), g['opt_vals'].tolist()))
+    Vd, gd, Id, Cd, Qd = g['out'].T
+    C, Q = ho.diode_charge_params(opt, Vd, gd, Id)
+    assert np.max(np.abs(C - Cd) / np.abs(Cd)) < 1e-13
+    assert np.max(np.abs(Q - Qd) / np.maximum(np.abs(Qd), 1e-30)) < 1e-12
