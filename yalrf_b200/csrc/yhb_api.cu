@@ -1184,7 +1184,7 @@ int eval_smem_bytes(const yhb_plan *pl, const Layout &L) {
 // the attribute is per device: set it on every call (cheap), like the fused launcher does
 int ensure_eval_attr(int bytes) {
     if (bytes > 48 * 1024)
-        YHB_CUDA(cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxEvalSmem));
+        YHB_CUDA(cudaFuncSetAttribute(k_eval<kEvalThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxEvalSmem));
     return 0;
 }
 
@@ -1551,7 +1551,9 @@ int run_loop(const yhb_plan *cpl, const yhb_params *p, const yhb_options *opt, L
         ea.cur = cur;
         {
             ProfScope ps(PK_EVAL, st);
-            k_eval<<<nactive, kEvalThreads, smem, st>>>(d, ws, ea);
+            // scratch in HBM = a large circuit: all the threads a CTA can have (scratch in shared memory: 256)
+            if (L.eval_smem) k_eval<kEvalThreads><<<nactive, kEvalThreads, smem, st>>>(d, ws, ea);
+            else k_eval<kEvalThreadsLarge><<<nactive, kEvalThreadsLarge, 0, st>>>(d, ws, ea);
         }
         YHB_CUDA(cudaGetLastError());
         YHB_CUDA(cudaMemcpyAsync(hc, ws.count, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -2133,7 +2135,7 @@ extern "C" int yhb_stage_assemble(const yhb_plan *pl, const yhb_params *p, void 
     ea.stage_alpha = alpha;
     const int smem = eval_smem_bytes(pl, L);
     if (int rc = ensure_eval_attr(smem)) return rc;
-    k_eval<<<p->batch, kEvalThreads, smem, st>>>(d, L.ws, ea);
+    k_eval<kEvalThreads><<<p->batch, kEvalThreads, smem, st>>>(d, L.ws, ea);
     dim3 ga(p->batch, (d.W + kAsmRows - 1) / kAsmRows);
     k_assemble<<<ga, 256, 0, st>>>(d, L.ws, ea);
     YHB_CUDA(cudaGetLastError());
