@@ -44,6 +44,14 @@ if os.path.exists(src):
         f.write('# serialised = the DC kernel cannot run beside the HB kernel here, so its share is its stand-alone duration)\n')
         for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('%-75s %5d %12.1f us %6.2f%%\n' % (k[:75], n, us, 100 * us / tot))
+        # the step's own kernels only (the list also holds the FP64-peak microbenchmark, the device-evaluation stage
+        # kernel of roofline_device_eval and torch's fills / copies, which run outside the timed steps)
+        own = ('k_fused', 'k_dc_', 'k_prepare', 'k_order', 'k_init', 'k_finish')
+        step = {k: v for k, v in agg.items() if any(o in k for o in own)}
+        stot = sum(v[1] for v in step.values())
+        f.write('# shares among the kernels of a step (compare roofline.share_serialised of bench.py):\n')
+        for k, (n, us) in sorted(step.items(), key=lambda kv: -kv[1][1]):
+            f.write('#   %-71s %5d %12.1f us %6.2f%%\n' % (k[:71], n, us, 100 * us / stot))
     print(open(out('bench_launch_list_summary.txt')).read())
 
 
