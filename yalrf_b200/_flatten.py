@@ -183,7 +183,11 @@ class ParamBlock:
 
     def finalize(self):
         # iac = ac * exp(j phase)  (MultiToneHarmonicBalance.py:653)
-        iac = self.src_ac * np.exp(1j * self.src_phase)
+        ph = self.src_phase
+        if ph.shape[0] > 1 and np.array_equal(ph, np.broadcast_to(ph[0], ph.shape)):
+            iac = self.src_ac * np.exp(1j * ph[0])[None, :]   # one phase per source for the whole batch: the same values
+        else:
+            iac = self.src_ac * np.exp(1j * ph)
         self.src_val[:, :, 1] = iac.real
         self.src_val[:, :, 2] = iac.imag
         for name in ('tones', 'lin_val', 'src_val', 'diode_par', 'bjt_par', 'cubic_par'):
